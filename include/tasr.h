@@ -1,0 +1,142 @@
+/* tasr.h — C ABI of the B200-native Telugu-ASR front-end hot path.
+ *
+ * The drop-in boundary for the reference's data-parallel front end:
+ *   waveform -> log-mel            (src/speech_featurizer.py:136-161, per utterance on CPU)
+ *   log-mel  -> subsampled [B,T3,d] (src/models/moonshine/encoder.py:50-71, Keras/cuDNN)
+ *   lengths  -> padding mask        (src/utils/math_util.py:20-32, encoder.py:43-48)
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  All data pointers are DEVICE
+ * pointers unless the name ends in `_host`.  Every launch entry point takes the CUDA
+ * stream to enqueue on and returns immediately (asynchronous); nothing allocates per
+ * call.  Return value: 0 = ok, otherwise a TASR_ERR_* code; `tasr_last_error()` gives
+ * the message for the calling thread.  Nothing throws across this boundary.
+ *
+ * Built for sm_100a only (libtasr_b200.so); there is no CPU fallback.
+ */
+#ifndef TASR_H_
+#define TASR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* tasr_stream_t; /* == cudaStream_t */
+
+enum {
+  TASR_OK = 0,
+  TASR_ERR_BAD_ARG = 1,      /* null pointer, negative size, inconsistent shapes            */
+  TASR_ERR_UNSUPPORTED = 2,  /* parameter combination the sm_100a kernels are not built for */
+  TASR_ERR_MISALIGNED = 3,   /* pointer / row stride not 16-byte aligned                     */
+  TASR_ERR_CUDA = 4          /* a CUDA runtime call failed; message carries cudaGetErrorString */
+};
+
+/* Activation codes of tasr_sepconv1d_f32 (Keras names: encoder.py:25,36). */
+enum { TASR_ACT_NONE = 0, TASR_ACT_TANH = 1, TASR_ACT_GELU_ERF = 2, TASR_ACT_RELU = 3 };
+
+/* Arithmetic of the pointwise (1x1) contraction. */
+enum {
+  TASR_MATH_FP32 = 0, /* FP32 FMA on CUDA cores (bit-for-bit deterministic, slowest)          */
+  TASR_MATH_TF32 = 1  /* tcgen05.mma kind::tf32, operands rounded to TF32 (rna), FP32 accum.  */
+};
+
+/* Feature parameters: the `speech_config` block of config/model.yaml:1-17 as the
+ * SpeechFeaturizer constructor derives them (src/speech_featurizer.py:41-65). */
+typedef struct TasrFeatParams {
+  int32_t sample_rate;      /* 16000                                                        */
+  int32_t frame_length;     /* int(round(sample_rate*frame_ms/1000))  = 400  (:46)           */
+  int32_t frame_step;       /* int(round(sample_rate*stride_ms/1000)) = 160  (:49)           */
+  int32_t fft_length;       /* enclosing power of two of frame_length = 512 (tf.signal.stft) */
+  int32_t num_mel_bins;     /* num_feature_bins = 80                                         */
+  int32_t normalize_signal; /* 1: x *= 1/(max|x|+1e-9) per utterance (:68-72)                */
+  int32_t log_base_e;       /* 0: log10 (log_base "10"), 1: natural log (:107-110)           */
+  int32_t pad_end;          /* must be 0 (config/model.yaml:8); 1 is TASR_ERR_UNSUPPORTED     */
+  float preemphasis;        /* 0.97; <= 0 disables (:74-79)                                  */
+  float output_floor;       /* 1e-9 (:109)                                                   */
+} TasrFeatParams;
+
+/* One SeparableConv1D layer (encoder.py:31-40), weights on the DEVICE, float32:
+ * dw [kernel, c_in] (Keras depthwise_kernel (k,Cin,1)), pw [c_in, c_out] (pointwise_kernel
+ * (1,Cin,Cout)), bias [c_out]. */
+typedef struct TasrSepConvLayer {
+  const float* dw;
+  const float* pw;
+  const float* bias;
+  int32_t c_in;
+  int32_t c_out;
+  int32_t kernel;     /* 9 */
+  int32_t stride;     /* 2 */
+  int32_t same;       /* 0 = "valid" (config/model.yaml:26); 1 = "same" is TASR_ERR_UNSUPPORTED in the conv kernels */
+  int32_t activation; /* TASR_ACT_* */
+} TasrSepConvLayer;
+
+typedef struct TasrFeaturizer TasrFeaturizer; /* opaque, owns the per-device constant tables */
+typedef struct TasrSepConvPlan TasrSepConvPlan; /* opaque, owns TF32-packed pointwise weights */
+
+int tasr_version(void);
+const char* tasr_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (all threads, all devices);
+ * bench.py reports the difference over the timed region as `gpu_launches`. */
+int64_t tasr_launch_count(void);
+
+/* Replaces SpeechFeaturizer.__init__ (src/speech_featurizer.py:19-66) plus the per-call
+ * tf.signal.hann_window / linear_to_mel_weight_matrix construction (:96-101, :114-120):
+ * the caller builds both tables ONCE in float32 on the host (same op order as TF) and the
+ * handle uploads them to the current device together with float64-derived FFT twiddles.
+ * hann_host [frame_length], mel_w_host [fft_length/2+1, num_mel_bins] row-major. */
+int tasr_featurizer_create(const TasrFeatParams* params, const float* hann_host,
+                           const float* mel_w_host, TasrFeaturizer** out);
+int tasr_featurizer_destroy(TasrFeaturizer* f);
+
+/* Replaces tf.reduce_max(tf.abs(signal)) (src/speech_featurizer.py:70), batched:
+ * peak[b] = max_{n < len[b]} |wav[b*row_stride + n]|.  peak is overwritten. */
+int tasr_absmax_f32(const float* wav, const int32_t* len, int32_t batch, int64_t row_stride,
+                    float* peak, tasr_stream_t stream);
+
+/* Replaces SpeechFeaturizer.call on each utterance (src/speech_featurizer.py:136-161:
+ * normalize_signal -> preemphasis_signal -> stft -> mel matmul -> logarithm) AND the
+ * zero-padded collate that follows it (src/dataset.py:173-175, 236-252).
+ * wav [batch, row_stride] (samples beyond len[b] are never read); peak from
+ * tasr_absmax_f32 (may be NULL when params.normalize_signal == 0);
+ * out [batch, t_max, num_mel_bins] float32: rows t < n_frames[b] hold log-mel, rows
+ * t >= n_frames[b] are written as 0.0; n_frames[b] = max(0, 1+(len[b]-frame_length)/frame_step)
+ * (src/speech_featurizer.py:163-166), clamped to t_max. */
+int tasr_logmel_f32(const TasrFeaturizer* f, const float* wav, const int32_t* len,
+                    const float* peak_or_null, int32_t batch, int64_t row_stride, float* out,
+                    int32_t t_max, int32_t* n_frames, tasr_stream_t stream);
+
+/* Replaces one tf.keras.layers.SeparableConv1D forward (encoder.py:31-40, called at :60):
+ * y[b,t,o] = act( sum_c ( sum_k x[b, stride*t+k, c] * dw[k,c] ) * pw[c,o] + bias[o] ),
+ * "valid" padding, t < t_out where t_out <= (t_in-kernel)/stride+1.  x [batch,t_in,c_in],
+ * y [batch,t_out,c_out].  The convolution runs over the whole zero-padded tensor, like the
+ * reference (no masking between layers).  math = TASR_MATH_FP32 here. */
+int tasr_sepconv1d_f32(const float* x, int32_t batch, int32_t t_in, const TasrSepConvLayer* layer,
+                       float* y, int32_t t_out, tasr_stream_t stream);
+
+/* TF32 tensor-core variant: the plan packs pw (rounded to TF32, UMMA K-major tiles) once. */
+int tasr_sepconv_plan_create(const TasrSepConvLayer* layer, TasrSepConvPlan** out, tasr_stream_t stream);
+int tasr_sepconv_plan_destroy(TasrSepConvPlan* plan);
+int tasr_sepconv1d_tf32(const TasrSepConvPlan* plan, const float* x, int32_t batch, int32_t t_in,
+                        float* y, int32_t t_out, tasr_stream_t stream);
+
+/* Replaces math_util.get_conv_length applied per layer (src/utils/math_util.py:20-32,
+ * encoder.py:60-68) and lengths_to_padding_mask (encoder.py:43-48).
+ * len_out [n_layers, batch] int32 gets the length after every layer, computed exactly as the
+ * reference does: int32(trunc(float32((L-k)/s + 1))) for valid, int32(ceil(L/s)) for same.
+ * mask (may be NULL) [batch, mask_width] float32 gets (t < len_last[b]).  The reference's
+ * mask width is max_b(len_last[b]); the caller passes that (or any upper bound). */
+int tasr_conv_lengths_mask(const int32_t* len_in, int32_t batch, int32_t n_layers,
+                           const int32_t* kernel_host, const int32_t* stride_host,
+                           const int32_t* same_host, int32_t* len_out, float* mask,
+                           int32_t mask_width, tasr_stream_t stream);
+
+/* Replaces ASRModel.create_masks + the mask->length reduction (model.py:80, encoder.py:53-56):
+ * n_frames[b] = #{t : any_f feat[b,t,f] != 0.0}.  feat [batch, t, f]. */
+int tasr_count_nonzero_frames(const float* feat, int32_t batch, int32_t t, int32_t f,
+                              int32_t* n_frames, tasr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TASR_H_ */

@@ -1,0 +1,81 @@
+// Shared helpers for the tasr C-ABI implementation (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/tasr.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "telugu_asr_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace tasr {
+
+void set_error(const char* fmt, ...);
+void count_launch();
+
+inline int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  set_error("%s", buf);
+  return code;
+}
+
+inline int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return TASR_OK;
+  return fail(TASR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define TASR_CUDA(call)                                            \
+  do {                                                             \
+    int _rc = ::tasr::check_cuda((call), #call);                   \
+    if (_rc != TASR_OK) return _rc;                                \
+  } while (0)
+
+#define TASR_LAUNCH_CHECK(name)                                    \
+  do {                                                             \
+    ::tasr::count_launch();                                        \
+    int _rc = ::tasr::check_cuda(cudaGetLastError(), name);        \
+    if (_rc != TASR_OK) return _rc;                                \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int sm_count();  // SMs of the current device (cached per device)
+
+// Fixed front-end geometry the kernels are specialised for (config/model.yaml:1-17).
+constexpr int kFrameLen = 400;
+constexpr int kFrameStep = 160;
+constexpr int kFft = 512;
+constexpr int kBins = 257;
+constexpr int kMel = 80;
+
+// Banded view of the [257,80] mel matrix: for mel bin m the non-zero weights are the
+// contiguous FFT bins [k0[m], k0[m]+4*n4[m]) (zero padded to a multiple of four).
+struct MelBands {
+  int32_t k0[kMel];
+  int32_t n4[kMel];
+  int32_t off4[kMel];  // offset of the first float4 of bin m in `w`
+  int32_t total4;
+};
+constexpr int kMelBandMaxW4 = 256;  // capacity in float4 (1024 weights; dense HTK needs ~160)
+
+}  // namespace tasr
+
+// Device-side handle contents.
+struct TasrFeaturizer {
+  TasrFeatParams p;
+  int device;
+  float* d_hwin;        // [512]  0.5*hann zero padded (0.5 folds the real-FFT split's 1/2)
+  float2* d_tw256;      // [256]  exp(-2*pi*i*j/256), float64-derived
+  float2* d_tw512;      // [256]  exp(-2*pi*i*j/512)
+  float4* d_band_w;     // [kMelBandMaxW4]
+  tasr::MelBands* d_bands;  // device copy of `bands`
+  tasr::MelBands bands; // host copy
+  float log_scale;      // log10(2) or ln(2)
+};

@@ -1,0 +1,69 @@
+"""The whole hot path as one object: waveforms -> log-mel -> 3x separable conv -> encoder input.
+
+Mirrors what the reference does across three places — the per-utterance featurizer call and
+padded_batch (src/dataset.py:171-175, 236-252), the mask derivation (model.py:80) and
+Conv1DSubsamplingLayer.call (encoder.py:50-71) — with every stage on the device."""
+from __future__ import annotations
+
+import os
+
+import torch
+import yaml
+
+from .speech_featurizer import SpeechFeaturizer
+from .subsampling import Conv1DSubsamplingLayer
+
+__all__ = ["FrontEnd", "REFERENCE_SPEECH_CONFIG", "REFERENCE_SUBSAMPLING_CONFIG", "load_reference_yaml"]
+
+# config/model.yaml:1-17
+REFERENCE_SPEECH_CONFIG = dict(
+    sample_rate=16000, frame_ms=25, stride_ms=10, num_feature_bins=80,
+    feature_type="log_mel_spectrogram", preemphasis=0.97, pad_end=False, lower_edge_hertz=0.0,
+    upper_edge_hertz=8000.0, output_floor=1e-9, log_base="10", nfft=512, normalize_signal=True,
+    normalize_zscore=False, normalize_min_max=False, padding=0.0)
+# config/model.yaml:21-27 (note the key is `activation`, which the layer does not read)
+REFERENCE_SUBSAMPLING_CONFIG = dict(
+    name="conv1d", kernel_size=[9, 9, 9], strides=[2, 2, 2], padding=["valid", "valid", "valid"],
+    activation=["gelu", "gelu", "gelu"])
+REFERENCE_D_MODEL = 192  # config/model.yaml:20
+
+
+def load_reference_yaml(path: str):
+    """Read speech_config / model_config.subsampling_config / d_model from a reference YAML
+    (config/model.yaml) with PyYAML — hydra is not needed for the values."""
+    with open(path) as fh:
+        cfg = yaml.safe_load(fh)
+    mc = cfg.get("model_config", {})
+    return dict(cfg["speech_config"]), dict(mc.get("subsampling_config", {})), int(mc.get("d_model", REFERENCE_D_MODEL))
+
+
+class FrontEnd:
+    def __init__(self, speech_config: dict | None = None, subsampling_config: dict | None = None,
+                 model_dim: int = REFERENCE_D_MODEL, math: str = "fp32", device=None, seed: int = 0):
+        self.featurizer = SpeechFeaturizer(**(speech_config or REFERENCE_SPEECH_CONFIG))
+        self.subsampling = Conv1DSubsamplingLayer(
+            model_dim=model_dim, subsampling_config=subsampling_config or REFERENCE_SUBSAMPLING_CONFIG,
+            input_dim=self.featurizer.num_feature_bins, math=math, seed=seed, name="asr_encoder_conv_subsampling")
+        self.device = torch.device(device) if device is not None else None
+
+    def set_weights(self, weights, device=None):
+        self.subsampling.set_weights(weights, device or self.device)
+
+    def __call__(self, wav: torch.Tensor, lengths: torch.Tensor | None = None, return_features: bool = False,
+                 max_length: int | None = None):
+        """wav [B, N_max] float32 CUDA, lengths [B] int32 CUDA ->
+        (encoder_input [B, T3, d], padding_mask [B, max(len3)], len3 [B] int32[, features, n_frames]).
+
+        `max_length` = max(lengths) when the caller knows it on the host (a collate does): the
+        feature tensor is then padded to exactly the batch maximum and the mask width is derived
+        on the host, so the step enqueues without any device->host synchronisation."""
+        t_max = None
+        if max_length is not None:
+            t_max = max(0, int(self.featurizer.get_nframes(int(max_length))))
+        feats, n_frames = self.featurizer.featurize_batch(wav, lengths, t_max=t_max)
+        out, mask, len_all = self.subsampling(feats, mask=n_frames, return_lengths=True,
+                                              max_frames=t_max if max_length is not None else None)
+        len3 = len_all[-1]
+        if return_features:
+            return out, mask, len3, feats, n_frames
+        return out, mask, len3

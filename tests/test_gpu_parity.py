@@ -1,0 +1,302 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C ABI of include/tasr.h
+(via the ctypes binding the Python mirror uses), against the CPU oracle on the same seeded inputs
+and against the committed fixtures under tests/golden/.
+
+Tolerances (BASELINE.json north_star): log-mel max-abs <= 1e-4 against the float64 oracle on the
+primary "tilt" distribution; on stress distributions whose own float32-vs-float64 band exceeds
+that (SURVEY.md hard part 1) the bound is 2.5x the float32 oracle's band.  Subsampled features:
+max-abs error / max-abs reference <= 1e-3 (TF32) and <= 2e-5 (FP32 path).  Frame counts, conv
+lengths and masks: bit-exact."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import telugu_asr_b200 as tasr
+from telugu_asr_b200 import _native
+
+pytestmark = pytest.mark.gpu
+
+LOGMEL_TOL = 1e-4
+SUB_TOL_TF32 = 1e-3
+SUB_TOL_FP32 = 2e-5
+
+
+def gpu(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+@pytest.fixture(scope="module")
+def feat():
+    return tasr.SpeechFeaturizer(**tasr.REFERENCE_SPEECH_CONFIG)
+
+
+def run_logmel(feat, wav, ln, dev):
+    out, nf = feat(gpu(wav, dev), gpu(ln, dev))
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), nf.cpu().numpy()
+
+
+def band_tol(wav, ln, ref64):
+    f32, _ = oracle.logmel_batch_ref(wav, ln, dtype=np.float32)
+    return max(LOGMEL_TOL, 2.5 * float(np.abs(f32 - ref64).max()))
+
+
+def test_native_library_is_loaded(cuda_device):
+    lib = _native.lib()
+    assert lib.tasr_version() >= 100
+    maps = open("/proc/self/maps").read()
+    assert "libtasr_b200.so" in maps
+    assert torch.cuda.get_device_capability(0)[0] >= 10, "these kernels are sm_100a only"
+
+
+def test_absmax(cuda_device):
+    lens = np.array([1, 3, 4, 5, 8191, 8192, 8193, 100000, 0], dtype=np.int32)
+    wav, ln = oracle.make_waveforms(lens, seed=3, dist="white")
+    wav[7, 99999] = -0.75
+    # samples beyond len[b] must not be read: poison them
+    for b, L in enumerate(lens):
+        wav[b, L:] = 7.0
+    peak = torch.empty(len(lens), dtype=torch.float32, device=cuda_device)
+    w = gpu(wav, cuda_device)
+    l = gpu(ln, cuda_device)
+    _native.check(_native.lib().tasr_absmax_f32(w.data_ptr(), l.data_ptr(), len(lens), w.stride(0), peak.data_ptr(),
+                                                _native.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = np.array([np.abs(wav[b, :L]).max() if L else 0.0 for b, L in enumerate(lens)], dtype=np.float32)
+    np.testing.assert_array_equal(peak.cpu().numpy(), ref)
+
+
+def test_logmel_config1_one_10s_utterance(feat, cuda_device):
+    """BASELINE.json configs[0]: the reference's own CPU-runnable case, 1 x 10 s."""
+    wav, ln = oracle.make_waveforms([160000], seed=0, dist="tilt")
+    out, nf = run_logmel(feat, wav, ln, cuda_device)
+    ref64 = oracle.logmel_ref(wav[0], dtype=np.float64)
+    assert out.shape == (1, 998, 80, 1) and nf.tolist() == [998]
+    err = np.abs(out[0, :, :, 0] - ref64).max()
+    assert err <= LOGMEL_TOL, err
+    # the 1-D call of src/dataset.py:171 gives the same values
+    one = feat(gpu(wav[0], cuda_device)).cpu().numpy()
+    np.testing.assert_array_equal(one, out[0, :, :, 0])
+
+
+def test_logmel_golden_fixtures(feat, cuda_device, golden_dir):
+    g = np.load(os.path.join(golden_dir, "logmel_tilt_1s.npz"))
+    wav, ln = oracle.make_waveforms(g["lengths"], seed=int(g["seed"]), dist=str(g["dist"]))
+    out, nf = run_logmel(feat, wav, ln, cuda_device)
+    assert np.abs(out[0, :, :, 0] - g["f64"]).max() <= LOGMEL_TOL
+    for dist in ("white", "half_silence"):
+        g = np.load(os.path.join(golden_dir, f"logmel_ragged_{dist}.npz"))
+        wav, ln = oracle.make_waveforms(g["lengths"], seed=int(g["seed"]), dist=dist)
+        out, nf = run_logmel(feat, wav, ln, cuda_device)
+        np.testing.assert_array_equal(nf, g["n_frames"])          # bit-exact frame counts
+        assert out.shape == g["f64"].shape
+        tol = band_tol(wav, ln, g["f64"])
+        assert np.abs(out - g["f64"]).max() <= tol
+        for b, t in enumerate(nf):                                  # collate padding is exactly 0.0
+            assert not out[b, t:].any()
+
+
+@pytest.mark.parametrize("dist", ["tilt", "white", "tone_noise", "half_silence", "zeros"])
+def test_logmel_distributions_ragged(feat, cuda_device, dist):
+    lens = [16000, 399, 400, 559, 560, 5281, 31999, 48000, 1, 0, 5119, 5120, 5121]
+    wav, ln = oracle.make_waveforms(lens, seed=17, dist=dist)
+    for b, L in enumerate(lens):      # padding samples are never read
+        wav[b, L:] = np.nan
+    out, nf = run_logmel(feat, wav, ln, cuda_device)
+    clean = np.nan_to_num(wav, nan=0.0)
+    ref64, nref = oracle.logmel_batch_ref(clean, ln, dtype=np.float64)
+    np.testing.assert_array_equal(nf, nref)
+    assert np.isfinite(out).all()
+    tol = band_tol(clean, ln, ref64)
+    assert np.abs(out - ref64).max() <= tol
+    if dist == "zeros":
+        for b, t in enumerate(nf):
+            assert np.abs(out[b, :t] + 9.0).max(initial=0.0) <= 2e-6
+    if dist == "half_silence":          # frames entirely inside the silent half sit on the floor
+        t_sil = (48000 // 2) // 160 + 3
+        assert np.abs(out[7, t_sil:nf[7]] + 9.0).max() <= 2e-6
+
+
+def test_logmel_config2_full_size(feat, cuda_device):
+    """BASELINE.json configs[1]: 64 x 10 s on one B200, full size, against the float32 and float64 oracles."""
+    wav, ln = oracle.make_waveforms([160000] * 64, seed=1, dist="tilt")
+    out, nf = run_logmel(feat, wav, ln, cuda_device)
+    assert out.shape == (64, 998, 80, 1) and (nf == 998).all()
+    worst = 0.0
+    for b in range(64):
+        ref = oracle.logmel_ref(wav[b], dtype=np.float64)
+        worst = max(worst, float(np.abs(out[b, :, :, 0] - ref).max()))
+    assert worst <= LOGMEL_TOL, worst
+
+
+def test_logmel_batch_invariance_and_prefix(feat, cuda_device):
+    """Per-utterance semantics on a padded batch: an utterance's features do not depend on what
+    else is in the batch, on N_max, or (when its peak lies in the prefix) on samples after a frame."""
+    lens = [30000, 12000, 20000]
+    wav, ln = oracle.make_waveforms(lens, seed=23, dist="tilt")
+    out, nf = run_logmel(feat, wav, ln, cuda_device)
+    for b, L in enumerate(lens):
+        alone = feat(gpu(wav[b, :L].copy(), cuda_device)).cpu().numpy()
+        np.testing.assert_array_equal(alone, out[b, : nf[b], :, 0])
+    # prefix property: cut after the peak sample, frames fully inside the prefix are unchanged
+    b = 0
+    pk = int(np.abs(wav[b, :lens[b]]).argmax())
+    cut = max(pk + 1, 8000)
+    cut = -(-cut // 4) * 4
+    pre = feat(gpu(wav[b, :cut].copy(), cuda_device)).cpu().numpy()
+    np.testing.assert_array_equal(pre, out[b, : pre.shape[0], :, 0])
+
+
+def test_logmel_long_batch_properties(feat, cuda_device):
+    """Config-4-shaped input at one rank's share (128 x 30 s): too large for the oracle in seconds,
+    so check shape, frame counts, sampled utterances against the oracle, and batch invariance via a
+    checksum of checksums between the full batch and two half batches."""
+    B = 128
+    base, _ = oracle.make_waveforms([480000] * 8, seed=3, dist="tilt")
+    wav = np.tile(base, (B // 8, 1))
+    wav *= (1.0 - 0.001 * (np.arange(B) % 7))[:, None].astype(np.float32)   # de-duplicate rows
+    ln = np.full(B, 480000, dtype=np.int32)
+    w = gpu(wav, cuda_device)
+    l = gpu(ln, cuda_device)
+    out, nf = feat(w, l)
+    assert tuple(out.shape) == (B, 2998, 80, 1) and bool((nf == 2998).all())
+    for b in (0, 77, 127):
+        ref = oracle.logmel_ref(wav[b], dtype=np.float64)
+        assert np.abs(out[b, :, :, 0].cpu().numpy() - ref).max() <= LOGMEL_TOL
+    full = out.double().sum(dim=(1, 2, 3))
+    h0, _ = feat(w[:64], l[:64])
+    h1, _ = feat(w[64:], l[64:])
+    halves = torch.cat([h0.double().sum(dim=(1, 2, 3)), h1.double().sum(dim=(1, 2, 3))])
+    assert torch.equal(full, halves)
+
+
+def _call_or_skip(fn, *args, **kw):
+    """A math mode the library reports as not built is a skip, not a silent fallback."""
+    try:
+        return fn(*args, **kw)
+    except NotImplementedError as e:   # pragma: no cover
+        pytest.skip(str(e))
+
+
+@pytest.mark.parametrize("math,tol", [("fp32", SUB_TOL_FP32), ("tf32", SUB_TOL_TF32)])
+def test_subsampling_golden(cuda_device, golden_dir, math, tol):
+    g = np.load(os.path.join(golden_dir, "subsample_2x3s.npz"))
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=int(g["weight_seed"]))
+    layer = tasr.Conv1DSubsamplingLayer(192, tasr.REFERENCE_SUBSAMPLING_CONFIG, math=math)
+    layer.set_weights(weights, cuda_device)
+    x = gpu(g["feat32"], cuda_device)
+    out, mask, len_all = _call_or_skip(layer, x, mask=gpu(g["n_frames"], cuda_device), return_lengths=True)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    assert out.shape == g["out64"].shape == (2, 31, 192)
+    rel = np.abs(out - g["out64"]).max() / np.abs(g["out64"]).max()
+    assert rel <= tol, rel
+    np.testing.assert_array_equal(len_all.cpu().numpy(), g["len_all"])      # bit-exact lengths
+    np.testing.assert_array_equal(mask.cpu().numpy(), g["mask"])            # bit-exact mask
+    # reference-style mask argument ([B,T,F] from create_masks) gives the same lengths
+    am = tasr.Conv1DSubsamplingLayer.create_audio_mask(x)
+    out2, mask2 = layer(x, mask=am)
+    np.testing.assert_array_equal(mask2.cpu().numpy(), g["mask"])
+    np.testing.assert_array_equal(out2.cpu().numpy(), out)
+    # mask=None -> no padding mask, like encoder.py:70
+    out3, mask3 = layer(x)
+    assert mask3 is None
+
+
+@pytest.mark.parametrize("math,tol", [("fp32", SUB_TOL_FP32), ("tf32", SUB_TOL_TF32)])
+def test_sepconv_single_layer_shapes(cuda_device, math, tol):
+    """Each layer shape of the stack on its own, odd/ragged T, through the C entry point."""
+    rng = np.random.default_rng(5)
+    for (cin, cout, act), T in zip([(80, 192, "tanh"), (192, 384, "gelu"), (384, 192, "gelu")], [203, 64 * 2 + 9, 10]):
+        x = rng.standard_normal((3, T, cin)).astype(np.float32)
+        dw = (rng.standard_normal((9, cin)) * 0.2).astype(np.float32)
+        pw = (rng.standard_normal((cin, cout)) / np.sqrt(cin)).astype(np.float32)
+        b = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+        ref = oracle.sepconv1d_ref(x, dw, pw, b, 2, "valid", act, dtype=np.float64)
+        layer = tasr.Conv1DSubsamplingLayer(cout, dict(kernel_size=[9], strides=[2], padding=["valid"], activations=[act]),
+                                            input_dim=cin, math=math)
+        layer.filters = [cout]
+        layer.set_weights([(dw, pw, b)], cuda_device)
+        out, _ = _call_or_skip(layer, gpu(x[..., None], cuda_device))
+        out = out.cpu().numpy()
+        assert out.shape == ref.shape
+        rel = np.abs(out - ref).max() / np.abs(ref).max()
+        assert rel <= tol, (cin, cout, rel)
+
+
+def test_conv_lengths_and_mask_bit_exact(cuda_device, golden_dir):
+    g = np.load(os.path.join(golden_dir, "lengths.npz"))
+    layer = tasr.Conv1DSubsamplingLayer(192, tasr.REFERENCE_SUBSAMPLING_CONFIG)
+    L = np.concatenate([g["small_in"], g["n_frames"], np.arange(64, 3100, 7, dtype=np.int32)]).astype(np.int32)
+    len_all, mask = layer.conv_lengths(gpu(L, cuda_device))
+    ref = oracle.conv_lengths_ref(L)
+    np.testing.assert_array_equal(len_all.cpu().numpy(), ref)
+    np.testing.assert_array_equal(mask.cpu().numpy(), oracle.lengths_to_padding_mask_ref(ref[-1]))
+    m2 = tasr.Conv1DSubsamplingLayer.lengths_to_padding_mask(gpu(np.array([3, 0, 5, -2], np.int32), cuda_device))
+    assert m2.cpu().numpy().tolist() == [[1, 1, 1, 0, 0], [0] * 5, [1] * 5, [0] * 5]
+    # "same" padding lengths (reference default config) are also float32-exact
+    same = tasr.Conv1DSubsamplingLayer(288, None)
+    la, _ = same.conv_lengths(gpu(L, cuda_device), with_mask=False)
+    np.testing.assert_array_equal(la.cpu().numpy(), oracle.conv_lengths_ref(L, padding=("same",) * 3))
+
+
+def test_full_pipeline_config3_full_size(cuda_device):
+    """BASELINE.json configs[2]: 256 x <=15 s, padded variable lengths and masks, log-mel + subsampling."""
+    from telugu_asr_b200.synth import draw_lengths
+    lens = draw_lengths(256, 16000, 240000, seed=2)
+    wav, ln = oracle.make_waveforms(lens, seed=2, dist="tilt")
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    fe = tasr.FrontEnd(math="fp32")
+    fe.set_weights(weights, cuda_device)
+    out, mask, len3, feats, nf = fe(gpu(wav, cuda_device), gpu(ln, cuda_device), return_features=True)
+    torch.cuda.synchronize()
+    assert tuple(feats.shape) == (256, 1498, 80, 1) and tuple(out.shape) == (256, 181, 192)
+    ref_feat, ref_nf = oracle.logmel_batch_ref(wav, ln, dtype=np.float32)
+    np.testing.assert_array_equal(nf.cpu().numpy(), ref_nf)
+    f = feats.cpu().numpy()
+    assert np.abs(f - ref_feat).max() <= LOGMEL_TOL
+    ref_out, ref_mask, ref_len = oracle.subsample_ref(ref_feat, ref_nf, weights, dtype=np.float32)
+    np.testing.assert_array_equal(len3.cpu().numpy(), ref_len[-1])
+    np.testing.assert_array_equal(mask.cpu().numpy(), ref_mask)
+    o = out.cpu().numpy()
+    # valid positions (what the encoder attends to) and padded positions (conv over zero padding) both match
+    rel = np.abs(o - ref_out).max() / np.abs(ref_out).max()
+    assert rel <= SUB_TOL_TF32, rel
+    fe_t = tasr.FrontEnd(math="tf32")
+    fe_t.set_weights(weights, cuda_device)
+    out_t, mask_t, len3_t = _call_or_skip(fe_t, gpu(wav, cuda_device), gpu(ln, cuda_device))
+    rel_t = np.abs(out_t.cpu().numpy() - ref_out).max() / np.abs(ref_out).max()
+    assert rel_t <= SUB_TOL_TF32, rel_t
+    assert torch.equal(mask_t, mask) and torch.equal(len3_t, len3)
+
+
+def test_error_behaviour(feat, cuda_device):
+    with pytest.raises(ValueError):
+        feat(torch.zeros((2, 3, 4), device=cuda_device))
+    with pytest.raises(ValueError):
+        feat(torch.zeros((2, 1600), device=cuda_device, dtype=torch.float64))
+    with pytest.raises(ValueError):
+        feat(torch.zeros((2, 1600), device=cuda_device), torch.zeros(3, dtype=torch.int32, device=cuda_device))
+    # misaligned row stride goes through the wrapper's aligned copy and still works
+    x = torch.zeros((2, 1603), device=cuda_device)
+    out, nf = feat(x, None)
+    assert tuple(out.shape) == (2, 8, 80, 1) and nf.tolist() == [8, 8]
+    # raw C ABI refuses it
+    lib = _native.lib()
+    rc = lib.tasr_absmax_f32(x.data_ptr(), nf.data_ptr(), 2, 1603, out.data_ptr(), _native.stream_ptr())
+    assert rc == _native.TASR_ERR_MISALIGNED
+    layer = tasr.Conv1DSubsamplingLayer(192, tasr.REFERENCE_SUBSAMPLING_CONFIG)
+    with pytest.raises(ValueError):
+        layer(torch.zeros((2, 100, 80), device=cuda_device))
+    with pytest.raises(ValueError):
+        layer(torch.zeros((2, 100, 64, 1), device=cuda_device))
+    # utterances shorter than the receptive field give zero-length outputs and empty masks, no crash
+    o, m = layer(torch.zeros((2, 20, 80, 1), device=cuda_device), mask=torch.tensor([20, 5], dtype=torch.int32, device=cuda_device))
+    assert o.shape[1] == 0 and m.shape == (2, 0)
+    # short batch: every utterance below one frame
+    o2, n2 = feat(torch.zeros((3, 396), device=cuda_device), None)
+    assert tuple(o2.shape) == (3, 0, 80, 1) and n2.tolist() == [0, 0, 0]
