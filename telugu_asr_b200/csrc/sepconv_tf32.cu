@@ -33,6 +33,7 @@ struct TasrSepConvPlan {
   int NT;
   int n_chunks;         // ceil(c_in / 32)
   float* d_bpack;       // [n_split][n_chunks][NT*32] shared-memory images of pw^T
+  void* kernel;         // template instance for (c_in, activation)
 };
 
 namespace {
@@ -128,13 +129,43 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float act_apply(float z, int act) {
-  switch (act) {
-    case TASR_ACT_TANH: return tanhf(z);
-    case TASR_ACT_GELU_ERF: return 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));
-    case TASR_ACT_RELU: return fmaxf(z, 0.0f);
-    default: return z;
-  }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// tanh(z) = 1 - 2/(1 + e^{2z}) on the SFU (ex2 + rcp): absolute error < 3e-7 over the whole range,
+// saturates correctly (e -> inf gives 1, e -> 0 gives -1).
+__device__ __forceinline__ float tanh_fast(float z) {
+  const float e = ex2_approx(z * 2.88539008177792681472f);   // 2*log2(e)
+  return fmaf(-2.0f, rcp_approx(1.0f + e), 1.0f);
+}
+// Exact-erf GELU (Keras approximate=False): 0.5 z (1 + erf(z/sqrt2)), with erf from Abramowitz &
+// Stegun 7.1.26 (|error| <= 1.5e-7): erfc(u) = t(a1 + t(a2 + t(a3 + t(a4 + t a5)))) e^{-u^2},
+// t = 1/(1 + p u), u = |z|/sqrt2.  gelu = z - (z/2) s for z >= 0 and (z/2) s for z < 0, s = erfc(u).
+__device__ __forceinline__ float gelu_erf_fast(float z) {
+  const float u = fabsf(z) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float s = p * t * ex2_approx(u * u * -1.44269504088896340736f);
+  const float hz = 0.5f * z;
+  return (z >= 0.0f) ? fmaf(-hz, s, z) : hz * s;
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_apply(float z) {
+  if (ACT == TASR_ACT_TANH) return tanh_fast(z);
+  if (ACT == TASR_ACT_GELU_ERF) return gelu_erf_fast(z);
+  if (ACT == TASR_ACT_RELU) return fmaxf(z, 0.0f);
+  return z;
 }
 
 struct SepArgs {
@@ -146,7 +177,11 @@ struct SepArgs {
   int32_t T_in, T_out, C_in, C_out, NT, n_chunks, act;
 };
 
+// CIN > 0 bakes the row stride into load immediates (the reference shapes 80/192/384 and the
+// model_dim=288 default 288/576); CIN == 0 reads it from the arguments.
+template <int CIN, int ACT>
 __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs a) {
+  const int C_in = CIN ? CIN : a.C_in;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   unsigned char* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -178,7 +213,8 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
   const uint32_t idesc = umma_idesc_tf32(kMT, NT);
   const int tw = t0 + warp * kRun;       // first output frame of this warp's run
   const int r0 = 2 * tw;                 // first input row of the run
-  const float* xrow = a.x + ((size_t)b * a.T_in + r0) * a.C_in + lane;
+  const float* xrow = a.x + ((size_t)b * a.T_in + r0) * C_in + lane;
+  const bool run_inside = (r0 + kWin <= a.T_in);   // warp-uniform: no row of this run is past the input
 
   for (int kc = 0; kc < a.n_chunks; ++kc) {
     const int s = kc & 1, use = kc >> 1;
@@ -192,15 +228,23 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
     }
     // ---- depthwise for channels [c0, c0+32) -> A[s] ----------------------------------------
     const int c0 = kc * kKC;
-    const int kvalid = min(kKC, a.C_in - c0);
+    const int kvalid = min(kKC, C_in - c0);
     const bool cok = lane < kvalid;
     float v[kWin];
-#pragma unroll
-    for (int i = 0; i < kWin; ++i)
-      v[i] = (cok && r0 + i < a.T_in) ? __ldg(xrow + c0 + (size_t)i * a.C_in) : 0.0f;
     float w[9];
+    if (run_inside && kvalid == kKC) {   // common case: unpredicated loads at immediate offsets
+      const float* xp = xrow + c0;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) w[k] = cok ? __ldg(a.dw + k * a.C_in + c0 + lane) : 0.0f;
+      for (int i = 0; i < kWin; ++i) v[i] = __ldg(xp + i * C_in);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) w[k] = __ldg(a.dw + k * C_in + c0 + lane);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kWin; ++i)
+        v[i] = (cok && r0 + i < a.T_in) ? __ldg(xrow + c0 + (size_t)i * C_in) : 0.0f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) w[k] = cok ? __ldg(a.dw + k * C_in + c0 + lane) : 0.0f;
+    }
     unsigned char* As = sA + s * kABytes;
 #pragma unroll
     for (int j = 0; j < kRun; ++j) {
@@ -239,11 +283,12 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
+        const float4 bv = *reinterpret_cast<const float4*>(sBias + g * 32 + 4 * i);
         float4 o;
-        o.x = act_apply(__uint_as_float(r[4 * i + 0]) + sBias[g * 32 + 4 * i + 0], a.act);
-        o.y = act_apply(__uint_as_float(r[4 * i + 1]) + sBias[g * 32 + 4 * i + 1], a.act);
-        o.z = act_apply(__uint_as_float(r[4 * i + 2]) + sBias[g * 32 + 4 * i + 2], a.act);
-        o.w = act_apply(__uint_as_float(r[4 * i + 3]) + sBias[g * 32 + 4 * i + 3], a.act);
+        o.x = act_apply<ACT>(__uint_as_float(r[4 * i + 0]) + bv.x);
+        o.y = act_apply<ACT>(__uint_as_float(r[4 * i + 1]) + bv.y);
+        o.z = act_apply<ACT>(__uint_as_float(r[4 * i + 2]) + bv.z);
+        o.w = act_apply<ACT>(__uint_as_float(r[4 * i + 3]) + bv.w);
         *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * i) = o;
       }
       __syncwarp();
@@ -278,6 +323,27 @@ __global__ void pack_pw_kernel(const float* __restrict__ pw, int C_in, int C_out
     const size_t base = ((size_t)nh * n_chunks + kc) * NT * kKC;
     const int phys = n * kKC + ((((cl >> 2) ^ (n & 7)) << 2) | (cl & 3));
     out[base + phys] = __uint_as_float(to_tf32(v));
+  }
+}
+
+typedef void (*SepKernel)(const SepArgs);
+template <int CIN>
+SepKernel pick_act(int act) {
+  switch (act) {
+    case TASR_ACT_TANH: return sepconv_tf32_kernel<CIN, TASR_ACT_TANH>;
+    case TASR_ACT_GELU_ERF: return sepconv_tf32_kernel<CIN, TASR_ACT_GELU_ERF>;
+    case TASR_ACT_RELU: return sepconv_tf32_kernel<CIN, TASR_ACT_RELU>;
+    default: return sepconv_tf32_kernel<CIN, TASR_ACT_NONE>;
+  }
+}
+SepKernel pick_kernel(int c_in, int act) {
+  switch (c_in) {
+    case 80: return pick_act<80>(act);
+    case 192: return pick_act<192>(act);
+    case 384: return pick_act<384>(act);
+    case 288: return pick_act<288>(act);
+    case 576: return pick_act<576>(act);
+    default: return pick_act<0>(act);
   }
 }
 
@@ -324,9 +390,11 @@ extern "C" int tasr_sepconv_plan_create(const TasrSepConvLayer* L, TasrSepConvPl
     count_launch();
     rc = check_cuda(cudaGetLastError(), "pack_pw_kernel");
   }
-  if (rc == TASR_OK)
-    rc = check_cuda(cudaFuncSetAttribute(sepconv_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(256)),
+  if (rc == TASR_OK) {
+    p->kernel = reinterpret_cast<void*>(pick_kernel(L->c_in, L->activation));
+    rc = check_cuda(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(256)),
                     "cudaFuncSetAttribute(sepconv_tf32_kernel)");
+  }
   if (rc != TASR_OK) { tasr_sepconv_plan_destroy(p); return rc; }
   *out = p;
   return TASR_OK;
@@ -353,7 +421,7 @@ extern "C" int tasr_sepconv1d_tf32(const TasrSepConvPlan* p, const float* x, int
   a.T_in = T_in; a.T_out = T_out; a.C_in = p->L.c_in; a.C_out = p->L.c_out; a.NT = p->NT;
   a.n_chunks = p->n_chunks; a.act = p->L.activation;
   dim3 grid((T_out + kMT - 1) / kMT, p->n_split, B);
-  sepconv_tf32_kernel<<<grid, kThreads, smem_bytes(p->NT), (cudaStream_t)stream>>>(a);
+  reinterpret_cast<SepKernel>(p->kernel)<<<grid, kThreads, smem_bytes(p->NT), (cudaStream_t)stream>>>(a);
   TASR_LAUNCH_CHECK("sepconv_tf32_kernel");
   return TASR_OK;
 }
