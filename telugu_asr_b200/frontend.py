@@ -39,7 +39,7 @@ def load_reference_yaml(path: str):
 
 class FrontEnd:
     def __init__(self, speech_config: dict | None = None, subsampling_config: dict | None = None,
-                 model_dim: int = REFERENCE_D_MODEL, math: str = "fp32", device=None, seed: int = 0):
+                 model_dim: int = REFERENCE_D_MODEL, math: str = "tf32", device=None, seed: int = 0):
         self.featurizer = SpeechFeaturizer(**(speech_config or REFERENCE_SPEECH_CONFIG))
         self.subsampling = Conv1DSubsamplingLayer(
             model_dim=model_dim, subsampling_config=subsampling_config or REFERENCE_SUBSAMPLING_CONFIG,

@@ -41,7 +41,7 @@ def get_conv_length(input_length: int, kernel_size: int, padding: str, strides: 
 class Conv1DSubsamplingLayer:
     def __init__(self, model_dim: int = 288, subsampling_config: dict | None = None,
                  kernel_regularizer=None, bias_regularizer=None, name: str = "conv1d_subsampling",
-                 input_dim: int = 80, math: str = "fp32", seed: int | None = None, **kwargs):
+                 input_dim: int = 80, math: str = "tf32", seed: int | None = None, **kwargs):
         subsampling_config = subsampling_config or {}
         self.name = name
         self.filters = [model_dim, 2 * model_dim, model_dim]                        # encoder.py:21
