@@ -89,6 +89,18 @@ int tasr_featurizer_create(const TasrFeatParams* params, const float* hann_host,
                            const float* mel_w_host, TasrFeaturizer** out);
 int tasr_featurizer_destroy(TasrFeaturizer* f);
 
+/* Device-side collate of raw audio (src/dataset.py:167-175 hands the featurizer one decoded
+ * utterance at a time; src/utils/data_util.py:31 decodes int16 PCM to float32 = sample/32768).
+ * `packed` holds the B utterances back to back on the DEVICE (only valid samples, so padding never
+ * crosses PCIe), utterance b at sample offset[b] (a multiple of 8, int64, device) with len[b]
+ * samples; they are written to wav[b*row_stride ...].  Samples beyond len[b] are not written (no
+ * kernel reads them).  max_len >= max_b len[b] sizes the grid.  The pcm16 variant converts exactly
+ * like tf.audio.decode_wav: float32(sample) * 2^-15. */
+int tasr_unpack_f32(const float* packed, const int64_t* offset, const int32_t* len, int32_t batch,
+                    int32_t max_len, float* wav, int64_t row_stride, tasr_stream_t stream);
+int tasr_unpack_pcm16(const int16_t* packed, const int64_t* offset, const int32_t* len, int32_t batch,
+                      int32_t max_len, float* wav, int64_t row_stride, tasr_stream_t stream);
+
 /* Replaces tf.reduce_max(tf.abs(signal)) (src/speech_featurizer.py:70), batched:
  * peak[b] = max_{n < len[b]} |wav[b*row_stride + n]|.  peak is overwritten. */
 int tasr_absmax_f32(const float* wav, const int32_t* len, int32_t batch, int64_t row_stride,

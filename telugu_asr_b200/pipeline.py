@@ -1,0 +1,107 @@
+"""Host-to-host front end: the reference's loader + featurizer + subsampling hand-off as a
+three-stage device pipeline.
+
+The reference decodes each wav file to float32 on a CPU thread, featurises it there, pads the batch
+and only then ships features to the GPU (src/dataset.py:167-197, 223-255; src/utils/data_util.py:31).
+Here the host hands over the raw utterances — packed, valid samples only, optionally still int16 PCM —
+and receives the encoder input, padding mask and lengths in pinned host memory:
+
+    copy-in stream   H2D of the packed batch                      (PackedBatch.to_device)
+    compute stream   unpack -> peak -> log-mel -> 3x sepconv -> lengths/mask
+    copy-out stream  D2H of [B,T3,d], mask, len3
+
+Slots are double buffered, so batch i+1 crosses PCIe while batch i computes and batch i-1 returns.
+Stream ordering is by CUDA events only; the host never blocks inside `submit`.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+from .collate import PackedBatch
+from .frontend import FrontEnd
+
+__all__ = ["FrontEndPipeline", "Ticket"]
+
+
+class Ticket:
+    """Result handle of one submitted batch; `wait()` blocks until its D2H has landed."""
+
+    def __init__(self, slot: int, done: torch.cuda.Event, out, mask, len3):
+        self.slot, self.done = slot, done
+        self._out, self._mask, self._len3 = out, mask, len3
+
+    def wait(self):
+        self.done.synchronize()
+        return self._out, self._mask, self._len3
+
+
+class FrontEndPipeline:
+    def __init__(self, frontend: FrontEnd, batch: int, n_max: int, device, pcm16: bool = True, slots: int = 2):
+        self.fe = frontend
+        self.device = torch.device(device)
+        self.batch, self.pcm16, self.slots = batch, pcm16, slots
+        self.staging = [PackedBatch(batch, n_max, self.device, pcm16=pcm16) for _ in range(slots)]
+        with torch.cuda.device(self.device):
+            self.s_in = torch.cuda.Stream()
+            self.s_out = torch.cuda.Stream()
+            self.ev_ready = [torch.cuda.Event() for _ in range(slots)]     # H2D of slot landed
+            self.ev_free = [torch.cuda.Event() for _ in range(slots)]      # packed device buffer consumed
+            self.ev_done = [torch.cuda.Event() for _ in range(slots)]      # D2H of slot landed
+            self.ev_comp = [torch.cuda.Event() for _ in range(slots)]      # compute of slot finished
+        self._host = [None] * slots    # pinned (out, mask, len3) per slot, sized on first use
+        self._used = [False] * slots
+        self.d2h_bytes = 0
+
+    def stage(self, slot: int, waveforms: Sequence) -> None:
+        """Host half of the collate: pack the utterances into the slot's pinned buffer."""
+        if self._used[slot]:
+            self.ev_free[slot].synchronize()     # the previous H2D+unpack of this slot must be over
+        self.staging[slot].fill(waveforms)
+
+    def _host_buffers(self, slot: int, out, mask, len3):
+        hb = self._host[slot]
+        if hb is None or hb[0].shape != out.shape or hb[1].shape != mask.shape:
+            hb = (torch.empty(out.shape, dtype=out.dtype).pin_memory(),
+                  torch.empty(mask.shape, dtype=mask.dtype).pin_memory(),
+                  torch.empty(len3.shape, dtype=len3.dtype).pin_memory())
+            self._host[slot] = hb
+        return hb
+
+    def submit(self, slot: int) -> Ticket:
+        """Enqueue H2D -> compute -> D2H for the staged slot; returns immediately."""
+        pb = self.staging[slot]
+        with torch.cuda.device(self.device):
+            comp = torch.cuda.current_stream()
+            if self._used[slot]:
+                self.s_in.wait_event(self.ev_free[slot])
+            with torch.cuda.stream(self.s_in):
+                pb.to_device(non_blocking=True)
+                self.ev_ready[slot].record(self.s_in)
+            comp.wait_event(self.ev_ready[slot])
+            wav, lens = pb.unpack()
+            self.ev_free[slot].record(comp)
+            out, mask, len3 = self.fe(wav, lens, max_length=pb.max_len)
+            self.ev_comp[slot].record(comp)
+            h_out, h_mask, h_len = self._host_buffers(slot, out, mask, len3)
+            self.s_out.wait_event(self.ev_comp[slot])
+            with torch.cuda.stream(self.s_out):
+                h_out.copy_(out, non_blocking=True)
+                h_mask.copy_(mask, non_blocking=True)
+                h_len.copy_(len3, non_blocking=True)
+                for t in (out, mask, len3):
+                    t.record_stream(self.s_out)
+                self.ev_done[slot].record(self.s_out)
+        self._used[slot] = True
+        self.d2h_bytes = (h_out.numel() + h_mask.numel()) * 4 + h_len.numel() * 4
+        return Ticket(slot, self.ev_done[slot], h_out, h_mask, h_len)
+
+    def run(self, waveforms: Sequence, slot: int = 0):
+        """Convenience, one batch, blocking: utterances -> (encoder_input, mask, len3) on the host."""
+        self.stage(slot, waveforms)
+        return self.submit(slot).wait()
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.staging[0].h2d_bytes

@@ -325,3 +325,42 @@ def test_error_behaviour(feat, cuda_device):
     # short batch: every utterance below one frame
     o2, n2 = feat(torch.zeros((3, 396), device=cuda_device), None)
     assert tuple(o2.shape) == (3, 0, 80, 1) and n2.tolist() == [0, 0, 0]
+
+
+@pytest.mark.parametrize("pcm16", [True, False])
+def test_device_collate_unpack_bit_exact(feat, cuda_device, pcm16):
+    """ragged packed host batch (int16 PCM or float32) -> padded device layout.
+    The int16 route is tf.audio.decode_wav's conversion (sample / 32768), exact in float32, so the
+    unpacked rows — and the log-mel computed from them — are bit-identical to the float32 route."""
+    from telugu_asr_b200.synth import to_pcm16
+    lens = [16000, 399, 1, 0, 5, 8191, 8192, 8193, 8, 7, 24001, 3]
+    wav, ln = oracle.make_waveforms(lens, seed=31, dist="tilt")
+    utts = [to_pcm16(wav[b, :L]) if pcm16 else wav[b, :L].copy() for b, L in enumerate(lens)]
+    pb = tasr.PackedBatch(len(lens), wav.shape[1], cuda_device, pcm16=pcm16)
+    pb.dev_wav.fill_(float("nan"))          # the unpack must not touch (and nothing may read) the padding
+    pb.fill(utts)
+    assert pb.h2d_bytes < wav.size * 4
+    pb.to_device()
+    w, l = pb.unpack()
+    torch.cuda.synchronize()
+    got = w.cpu().numpy()
+    np.testing.assert_array_equal(l.cpu().numpy(), ln)
+    for b, L in enumerate(lens):
+        np.testing.assert_array_equal(got[b, :L], wav[b, :L])
+        assert np.isnan(got[b, L:]).all()
+    out, nf = feat(w, l)
+    ref, nref = feat(gpu(wav, cuda_device), gpu(ln, cuda_device))
+    assert torch.equal(out, ref) and torch.equal(nf, nref)
+    # int16 extremes decode like decode_wav: -32768 -> -1.0, 32767 -> 32767/32768
+    if pcm16:
+        ext = np.array([-32768, 32767, 0, 1, -1, 12345, -12345, 2], dtype=np.int16)
+        pb2 = tasr.PackedBatch(1, 8, cuda_device, pcm16=True)
+        pb2.fill([ext])
+        pb2.to_device()
+        w2, _ = pb2.unpack()
+        np.testing.assert_array_equal(w2.cpu().numpy()[0, :8], ext.astype(np.float32) / np.float32(32768.0))
+    # C-ABI argument validation
+    lib = _native.lib()
+    rc = lib.tasr_unpack_f32(pb.dev_packed.data_ptr(), pb.dev_off.data_ptr(), pb.dev_len.data_ptr(), len(lens),
+                             pb.n_max + 4, pb.dev_wav.data_ptr(), pb.n_max, _native.stream_ptr())
+    assert rc == _native.TASR_ERR_BAD_ARG

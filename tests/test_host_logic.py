@@ -148,3 +148,14 @@ def test_synth_is_seeded_pcm_exact_and_aligned():
     assert not z.any()
     with pytest.raises(ValueError):
         make_waveforms([10], dist="pink")
+
+
+def test_packed_batch_offsets_are_aligned_and_disjoint():
+    lens = [16000, 399, 1, 0, 5, 8191, 8192, 8193]
+    off, used = tasr.PackedBatch.offsets_for(lens)
+    assert (off % 8 == 0).all() and off[0] == 0
+    ends = off + np.asarray(lens)
+    assert (ends[:-1] <= off[1:]).all() and used >= ends[-1] and used % 8 == 0
+    assert used - sum(lens) < 8 * len(lens)
+    o0, u0 = tasr.PackedBatch.offsets_for([])
+    assert len(o0) == 0 and u0 == 0
