@@ -88,6 +88,9 @@ int64_t tasr_launch_count(void);
 int tasr_featurizer_create(const TasrFeatParams* params, const float* hann_host,
                            const float* mel_w_host, TasrFeaturizer** out);
 int tasr_featurizer_destroy(TasrFeaturizer* f);
+/* 1 when the handle's mel matrix has the config/model.yaml sparsity structure and tasr_logmel_f32
+ * runs the fully unrolled projection, 0 when it runs the generic banded loop, < 0 on a null handle. */
+int tasr_featurizer_uses_fixed_mel(const TasrFeaturizer* f);
 
 /* Device-side collate of raw audio (src/dataset.py:167-175 hands the featurizer one decoded
  * utterance at a time; src/utils/data_util.py:31 decodes int16 PCM to float32 = sample/32768).

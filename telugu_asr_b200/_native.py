@@ -40,6 +40,7 @@ _SIGNATURES = {
     "tasr_launch_count": (C.c_int64, []),
     "tasr_featurizer_create": (C.c_int, [C.POINTER(TasrFeatParams), _vp, _vp, C.POINTER(_vp)]),
     "tasr_featurizer_destroy": (C.c_int, [_vp]),
+    "tasr_featurizer_uses_fixed_mel": (C.c_int, [_vp]),
     "tasr_unpack_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     "tasr_unpack_pcm16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     "tasr_absmax_f32": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),

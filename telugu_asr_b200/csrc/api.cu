@@ -56,6 +56,8 @@ extern "C" int tasr_featurizer_create(const TasrFeatParams* p, const float* hann
                 p->frame_length, p->frame_step, p->fft_length, p->num_mel_bins);
   if (p->pad_end) return fail(TASR_ERR_UNSUPPORTED, "tasr_featurizer_create: pad_end=True is not built");
   if (!(p->output_floor > 0.0f)) return fail(TASR_ERR_BAD_ARG, "tasr_featurizer_create: output_floor must be > 0");
+  if (p->output_floor < 1.17549435e-38f)
+    return fail(TASR_ERR_UNSUPPORTED, "tasr_featurizer_create: output_floor below FLT_MIN (the log uses a flush-to-zero MUFU)");
 
   // Banded mel structure from the dense matrix the caller built (values are used verbatim).
   MelBands bands;
@@ -102,6 +104,7 @@ extern "C" int tasr_featurizer_create(const TasrFeatParams* p, const float* hann
   f->p = *p;
   f->bands = bands;
   f->log_scale = p->log_base_e ? 0.69314718055994530942f : 0.30102999566398119521f;
+  f->mel_fixed = tasr_mel_fixed_from_dense(mel_w_host, f->mel_fixed_w) ? 1 : 0;
   int rc = check_cuda(cudaGetDevice(&f->device), "cudaGetDevice");
   if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&f->d_hwin, kFft * sizeof(float)), "cudaMalloc hwin");
   if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&f->d_tw256, 256 * sizeof(float2)), "cudaMalloc tw256");
@@ -128,6 +131,8 @@ extern "C" int tasr_featurizer_destroy(TasrFeaturizer* f) {
   delete f;
   return TASR_OK;
 }
+
+extern "C" int tasr_featurizer_uses_fixed_mel(const TasrFeaturizer* f) { return f ? f->mel_fixed : -1; }
 
 // ---------------------------------------------------------------------------------------
 // Lengths after each conv layer + padding mask (src/utils/math_util.py:20-32, encoder.py:43-48)

@@ -78,4 +78,9 @@ struct TasrFeaturizer {
   tasr::MelBands* d_bands;  // device copy of `bands`
   tasr::MelBands bands; // host copy
   float log_scale;      // log10(2) or ln(2)
+  int mel_fixed;        // 1: the matrix has the compiled-in config/model.yaml structure (mel_geometry.inc)
+  float mel_fixed_w[512];  // wr[256] | wf[256], per FFT bin (kernel-parameter constants of the unrolled projection)
 };
+
+// logmel.cu: true (and wr_wf_512 filled) when the dense [257,80] matrix has the compiled-in structure.
+bool tasr_mel_fixed_from_dense(const float* mel_w_host, float* wr_wf_512);

@@ -5,44 +5,64 @@
 // matmul -> log10(max(.,1e-9))) and the zero-padded collate of src/dataset.py:236-252.
 //
 // Work decomposition
+//   items = (a) the VALID 32-frame tiles of every utterance, dealt round-robin to the persistent
+//           CTAs (every CTA gets the same number of them +-1: a ragged batch stays balanced), and
+//           (b) the collate padding (rows t >= n_frames[b]), zero-filled in 128-row chunks that are
+//           dealt round-robin the same way, first, so the stores drain under the FFT work;
 //   tile  = 32 consecutive frames of one utterance (5360 samples, staged once in shared memory
-//           with gain and pre-emphasis applied in exactly the reference's float32 op order);
+//           with gain and pre-emphasis applied in exactly the reference's float32 op order; the
+//           next tile's samples are prefetched into L2 while this one computes);
 //   FFT   = 16 lanes per frame (two frames per warp).  The 512-point real FFT is a 256-point
 //           complex FFT of z[m] = y[2m] + i*y[2m+1] done as 16x16: radix-16 in registers,
 //           twiddle, 16x16 transpose through a padded per-warp scratch, radix-16 again; then the
 //           real-FFT split, where lane t and lane 16-t exchange eight values by warp shuffle and
 //           each forms |X[k]|^2 and |X[256-k]|^2 for its eight k;
-//   mel   = lane <-> frame, warp <-> 10 mel bins; banded FP32 FMAs over the 502 non-zero weights
-//           (weights broadcast from shared memory, power rows read conflict-free, stride 261);
-//   out   = log, staged through shared memory, written with coalesced 128-bit stores; rows
-//           t >= n_frames[b] are written as 0.0 (the collate padding value).
+//   mel   = lane <-> frame, warp <-> a contiguous group of mel bins.  For the config/model.yaml
+//           filterbank the sparsity structure is compiled in (mel_geometry.inc): every power bin
+//           is loaded once and feeds its two adjacent triangles with weights read straight from
+//           the kernel-parameter constant bank, fully unrolled (3 instructions per FFT bin).  Any
+//           other triangular filterbank takes the generic banded loop;
+//   out   = log, staged through shared memory, written with coalesced 128-bit stores.
 //
-// Per-lane constants (half-window, transpose twiddles, split twiddle) live in registers for the
-// whole persistent loop over tiles.  Twiddles are float64-derived tables.
+// Per-lane constants (half-window, transpose twiddles) live in registers for the whole
+// persistent loop.  Twiddles are float64-derived tables.
 #include "common.cuh"
 
 using namespace tasr;
 
 namespace {
 
+#include "mel_geometry.inc"
+
 constexpr int kTileFrames = 32;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kWavSmem = 5376;          // (32-1)*160+400 = 5360, +16 floats lanes 8..15 touch at m2=12
+constexpr int kWavSlots = kWavSmem / 4 / kThreads + 1;   // float4 slots per thread (6; 1344 = 5.25 * 256)
 constexpr int kScrStride = 17;          // float2 units; odd -> conflict-free transposed reads
 constexpr int kScrPerFrame = 16 * kScrStride;
-constexpr int kPStride = kBins + 4;     // 261, odd; columns 257..260 stay zero (band padding)
+constexpr int kPStride = kBins + 4;     // 261, odd; columns 257..260 stay zero (band padding of the generic path)
 constexpr int kOutStride = kMel + 1;    // 81
+constexpr int kPadChunkRows = 128;      // rows of collate padding zero-filled per work item
 
 struct __align__(16) Smem {
   float wav[kWavSmem];
   float2 scr[kWarps * 2 * kScrPerFrame];   // also the [32][81] output staging tile
   float P[kTileFrames * kPStride];
-  float4 band_w[kMelBandMaxW4];
-  MelBands bands;
+  float2 tw512[136];                       // W512^k, k = 0..128
+  float4 band_w[kMelBandMaxW4];            // generic path only
+  MelBands bands;                          // generic path only
 };
 static_assert(sizeof(float) * kTileFrames * kOutStride <= sizeof(float2) * kWarps * 2 * kScrPerFrame,
               "output staging must fit in the transpose scratch");
+
+// Per-FFT-bin weights of the fixed-geometry mel projection, passed BY VALUE as a kernel parameter so
+// that they sit in the constant bank and FFMA reads them as operands (no load instruction):
+// wr[k] = W[k, seg(k)] (rising side of bin seg(k)), wf[k] = W[k, seg(k)-1] (falling side of the bin below).
+struct MelFixedW {
+  float wr[256];
+  float wf[256];
+};
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -83,22 +103,18 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 }
 #define X16(v, k) (v)[((k) >> 2) + 4 * ((k) & 3)]
 
-// exp(-2*pi*i*j/32), j = 0..7 (folded to immediates after unrolling).
-__device__ __forceinline__ float2 w32(int j) {
-  switch (j) {
-    case 1: return make_float2(0.98078528040323044913f, -0.19509032201612826785f);
-    case 2: return make_float2(0.92387953251128675613f, -0.38268343236508977173f);
-    case 3: return make_float2(0.83146961230254523708f, -0.55557023301960222474f);
-    case 4: return make_float2(0.70710678118654752440f, -0.70710678118654752440f);
-    case 5: return make_float2(0.55557023301960222474f, -0.83146961230254523708f);
-    case 6: return make_float2(0.38268343236508977173f, -0.92387953251128675613f);
-    case 7: return make_float2(0.19509032201612826785f, -0.98078528040323044913f);
-    default: return make_float2(1.0f, 0.0f);
-  }
-}
-
 __device__ __forceinline__ void st_global_v4(float* p, float4 v) {
   asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// log2 of a NORMAL positive float (the argument is clamped to output_floor >= FLT_MIN first, so the
+// denormal rescue sequence of __log2f is dead weight): one MUFU.
+__device__ __forceinline__ float lg2_normal(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 struct LogmelArgs {
@@ -113,16 +129,74 @@ struct LogmelArgs {
   const float4* band_w;
   const MelBands* bands;
   int64_t row_stride;
-  int32_t B, T_max, tiles_per_row, total_tiles;
+  int32_t B, T_max, tiles_per_row;
   int32_t normalize;
   float preemph, floor_, log_scale;
 };
 
-__global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelArgs a) {
+__device__ __forceinline__ int frames_of(int n, int T_max) {
+  const int Tb = (n >= kFrameLen) ? 1 + (n - kFrameLen) / kFrameStep : 0;
+  return min(Tb, T_max);
+}
+
+// ---- fixed-geometry mel projection (config/model.yaml filterbank), fully unrolled ------------------
+// Warp W owns mel bins [kMelGrp[W], kMelGrp[W+1]).  It walks segments m = first..last+1; in segment m
+// each power bin k is loaded once and accumulated into bin m (rising weight) and bin m-1 (falling
+// weight); bin m-1 is complete when segment m ends.  Summation is in ascending k, like a dot product.
+template <int M, int M0, int M1>
+struct MelSeg {
+  static __device__ __forceinline__ void run(const float* __restrict__ Prow, const MelFixedW& w, float* __restrict__ srow,
+                                             float floor_, float scale, float acc_prev) {
+    float acc_cur = 0.0f;
+    constexpr int kBegin = kMelSegStart[M], kEnd = kMelSegStart[M + 1];
+#pragma unroll
+    for (int k = kBegin; k < kEnd; ++k) {
+      const float p = Prow[k];
+      if (M < M1) acc_cur = fmaf(p, w.wr[k], acc_cur);
+      if (M > M0) acc_prev = fmaf(p, w.wf[k], acc_prev);
+    }
+    if (M > M0) srow[M - 1] = lg2_normal(fmaxf(acc_prev, floor_)) * scale;
+    if constexpr (M < M1) MelSeg<M + 1, M0, M1>::run(Prow, w, srow, floor_, scale, acc_cur);
+  }
+};
+
+template <int W>
+__device__ __forceinline__ void mel_fixed_group(const float* Prow, const MelFixedW& w, float* srow, float floor_, float scale) {
+  MelSeg<kMelGrp[W], kMelGrp[W], kMelGrp[W + 1]>::run(Prow, w, srow, floor_, scale, 0.0f);
+}
+
+template <bool FIXED>
+__global__ void __launch_bounds__(kThreads, 2)
+logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelFixedW mw) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = lane & 15, half = lane >> 4;
+
+  // ---- n_frames (src/speech_featurizer.py:163-166) -------------------------------------------
+  for (int b = blockIdx.x * kThreads + tid; b < a.B; b += gridDim.x * kThreads) a.n_frames[b] = frames_of(a.len[b], a.T_max);
+
+  // ---- (b) collate padding: rows beyond the last valid tile of every utterance, 128-row chunks ----
+  {
+    int b = 0, cum = 0, cnt = -1, vt = 0;   // cnt < 0: utterance b not examined yet
+    for (int j = blockIdx.x;; j += gridDim.x) {
+      while (b < a.B) {
+        if (cnt < 0) {
+          vt = (frames_of(a.len[b], a.T_max) + kTileFrames - 1) / kTileFrames;
+          const int pad_rows = a.T_max - vt * kTileFrames;
+          cnt = pad_rows > 0 ? (pad_rows + kPadChunkRows - 1) / kPadChunkRows : 0;
+        }
+        if (j < cum + cnt) break;
+        cum += cnt; ++b; cnt = -1;
+      }
+      if (b >= a.B) break;
+      const int r0 = vt * kTileFrames + (j - cum) * kPadChunkRows;
+      const int rows = min(kPadChunkRows, a.T_max - r0);
+      float* dst = a.out + ((size_t)b * a.T_max + r0) * kMel;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = tid; i < rows * (kMel / 4); i += kThreads) st_global_v4(dst + 4 * i, z);
+    }
+  }
 
   // ---- per-lane constants ----------------------------------------------------------------
   float2 hw[13];
@@ -131,38 +205,53 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelArgs a)
   float2 tw[16];
 #pragma unroll
   for (int k2 = 1; k2 < 16; ++k2) tw[k2] = a.tw256[(t * k2) & 255];
-  const float2 base = a.tw512[t];
-  const float2 w0 = (t == 0) ? make_float2(0.0f, -1.0f) : base;
   const int partner = (lane & 16) | ((16 - t) & 15);
 
-  for (int i = tid; i < kMelBandMaxW4; i += kThreads) S.band_w[i] = a.band_w[i];
-  {
+  for (int i = tid; i <= 128; i += kThreads) S.tw512[i] = a.tw512[i];
+  if (!FIXED) {
+    for (int i = tid; i < kMelBandMaxW4; i += kThreads) S.band_w[i] = a.band_w[i];
     const int32_t* src = reinterpret_cast<const int32_t*>(a.bands);
     int32_t* dst = reinterpret_cast<int32_t*>(&S.bands);
     for (int i = tid; i < (int)(sizeof(MelBands) / 4); i += kThreads) dst[i] = src[i];
+    for (int i = tid; i < kTileFrames * 4; i += kThreads) S.P[(i >> 2) * kPStride + kBins + (i & 3)] = 0.0f;
   }
-  for (int i = tid; i < kTileFrames * 4; i += kThreads) S.P[(i >> 2) * kPStride + kBins + (i & 3)] = 0.0f;
   __syncthreads();
 
   float2* scr = S.scr + (warp * 2 + half) * kScrPerFrame;
   float* stage = reinterpret_cast<float*>(S.scr);
+  const float2* twp = S.tw512 + t;           // W512^(t+16j) at twp[16j]; lane t=0 uses W512^128 for j=0
+  const int tw0 = (t == 0) ? 128 : 0;
 
-  for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-    const int b = tile / a.tiles_per_row;
-    const int tf = tile - b * a.tiles_per_row;
+  // ---- (a) valid tiles, round-robin ------------------------------------------------------------
+  // `nx` runs one item ahead of `cu` so that the next tile's samples can be prefetched into L2.
+  int nb = 0, ncum = 0, ncnt = -1;      // walker state: utterance, valid tiles before it, its valid tiles
+  auto advance = [&](int jj) -> bool {  // positions (nb, ncum) on valid tile jj; false when past the end
+    while (nb < a.B) {
+      if (ncnt < 0) ncnt = (frames_of(a.len[nb], a.T_max) + kTileFrames - 1) / kTileFrames;
+      if (jj < ncum + ncnt) return true;
+      ncum += ncnt; ++nb; ncnt = -1;
+    }
+    return false;
+  };
+  int j = blockIdx.x;
+  bool more = advance(j);
+  while (more) {
+    const int b = nb;
+    const int tf = j - ncum;
+    j += gridDim.x;
+    more = advance(j);
+
     const int n = a.len[b];
-    int Tb = (n >= kFrameLen) ? 1 + (n - kFrameLen) / kFrameStep : 0;
-    Tb = min(Tb, a.T_max);
-    if (tf == 0 && tid == 0) a.n_frames[b] = Tb;
+    const int Tb = frames_of(n, a.T_max);
     const int f0 = tf * kTileFrames;
     const int rows = min(kTileFrames, a.T_max - f0);
-    const int nvalid = max(0, min(kTileFrames, Tb - f0));
+    const int nvalid = min(kTileFrames, Tb - f0);   // >= 1: only valid tiles are enumerated
     float* orow = a.out + ((size_t)b * a.T_max + f0) * kMel;
 
-    if (nvalid == 0) {  // whole tile is collate padding
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int i = tid; i < rows * (kMel / 4); i += kThreads) st_global_v4(orow + 4 * i, z);
-      continue;
+    if (more && tid < 168) {  // next tile: 5360 samples = 167.5 lines of 128 B
+      const float* nrow = a.wav + (size_t)nb * a.row_stride;
+      const int ns = (j - ncum) * kTileFrames * kFrameStep + tid * 32;
+      if (ns < a.len[nb]) prefetch_l2(nrow + ns);
     }
 
     // ---- stage the tile: gain, pre-emphasis (reference float32 op order), to shared --------
@@ -173,23 +262,35 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelArgs a)
       float g = 1.0f;
       if (a.normalize) g = __fdiv_rn(1.0f, __fadd_rn(a.peak[b], 1e-9f));  // :70
       const float c = a.preemph;
-      for (int i4 = tid; i4 < kWavSmem / 4; i4 += kThreads) {
+      float4 x[kWavSlots];
+      float xp[kWavSlots];
+#pragma unroll
+      for (int u = 0; u < kWavSlots; ++u) {     // all loads first: 6 x 128-bit + 6 x 32-bit in flight per thread
+        const int i4 = tid + u * kThreads;
         const int s = s0 + 4 * i4;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool in = (4 * i4 < count);
-        if (in) x = *reinterpret_cast<const float4*>(row + s);
-        x.x = __fmul_rn(x.x, g); x.y = __fmul_rn(x.y, g); x.z = __fmul_rn(x.z, g); x.w = __fmul_rn(x.w, g);  // :71
-        float xp = __shfl_up_sync(0xffffffffu, x.w, 1);
-        if (lane == 0) xp = (in && s > 0) ? __fmul_rn(row[s - 1], g) : 0.0f;
-        float4 y = x;
-        if (c > 0.0f) {  // :75-79  y[0]=x[0]; y[n]=x[n]-c*x[n-1], product and difference rounded separately
-          y.x = (s > 0) ? __fsub_rn(x.x, __fmul_rn(c, xp)) : x.x;
-          y.y = __fsub_rn(x.y, __fmul_rn(c, x.x));
-          y.z = __fsub_rn(x.z, __fmul_rn(c, x.y));
-          y.w = __fsub_rn(x.w, __fmul_rn(c, x.z));
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xp[u] = 0.0f;
+        if (4 * i4 < count) {
+          x[u] = *reinterpret_cast<const float4*>(row + s);
+          if (s > 0) xp[u] = row[s - 1];
         }
-        if (!in) y = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(S.wav + 4 * i4) = y;
+      }
+#pragma unroll
+      for (int u = 0; u < kWavSlots; ++u) {
+        const int i4 = tid + u * kThreads;
+        if (4 * i4 < count + 16 && i4 < kWavSmem / 4) {     // [count, count+16) must be finite zeros (window tail)
+          float4 v = x[u];
+          v.x = __fmul_rn(v.x, g); v.y = __fmul_rn(v.y, g); v.z = __fmul_rn(v.z, g); v.w = __fmul_rn(v.w, g);  // :71
+          float4 y = v;
+          if (c > 0.0f) {  // :75-79  y[0]=x[0]; y[n]=x[n]-c*x[n-1], product and difference rounded separately
+            const float vp = __fmul_rn(xp[u], g);
+            y.x = (s0 + 4 * i4 > 0) ? __fsub_rn(v.x, __fmul_rn(c, vp)) : v.x;
+            y.y = __fsub_rn(v.y, __fmul_rn(c, v.x));
+            y.z = __fsub_rn(v.z, __fmul_rn(c, v.y));
+            y.w = __fsub_rn(v.w, __fmul_rn(c, v.z));
+          }
+          *reinterpret_cast<float4*>(S.wav + 4 * i4) = y;
+        }
       }
     }
     __syncthreads();
@@ -200,6 +301,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelArgs a)
       const int fA = pass * 8 + warp;
       if (fA >= nvalid) continue;  // both of this warp's frames are padding (warp-uniform)
       const int fr = fA + 16 * half;
+      // frame fA+16 may be beyond nvalid: its samples are then stale but finite (a previous tile's, or the
+      // zero-initialised buffer) and its P row is never read by a valid output row.
       const float* frp = S.wav + fr * kFrameStep + 2 * t;
       float2 v[16];
 #pragma unroll
@@ -219,7 +322,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelArgs a)
       for (int n1 = 0; n1 < 16; ++n1) v[n1] = scr[t * kScrStride + n1];
       fft16(v);  // X16(v,k1) = Z[t + 16*k1] (half scaled)
 
-      float* Prow = S.P + fr * kPStride;
+      float* Pa = S.P + fr * kPStride + t;          // P[k],     k = t + 16j
+      float* Pb = S.P + fr * kPStride + 256 - t;    // P[256-k]
       // real-FFT split: pairs (k, 256-k), k = t+16j, j=0..7; partner lane holds Z[256-k] at k1=15-j
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -232,46 +336,65 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelArgs a)
         }
         const float er = za.x + zb.x, ei = za.y - zb.y;      // E' = Z[k] + conj(Z[256-k])
         const float dr = za.x - zb.x, di = za.y + zb.y;      // D  = Z[k] - conj(Z[256-k])
-        float2 o = make_float2(di, -dr);                     // O' = -i*D
-        if (j > 0) o = cmul(o, w32(j));
-        const float2 tt = cmul(o, (j == 0) ? w0 : base);     // W512^k * O'
+        const float2 wk = (j == 0) ? twp[tw0] : twp[16 * j];  // W512^k
+        const float2 tt = cmul(make_float2(di, -dr), wk);    // W512^k * (-i*D)
         const float ar = er + tt.x, ai = ei + tt.y;          // X[k]
         const float br = er - tt.x, bi = ei - tt.y;          // conj(X[256-k])
-        const int ka = (j == 0) ? ((t == 0) ? 128 : t) : t + 16 * j;
-        Prow[ka] = ar * ar + ai * ai;
-        Prow[256 - ka] = br * br + bi * bi;
+        const float pa = ar * ar + ai * ai, pb = br * br + bi * bi;
+        if (j == 0) {
+          const int ka = (t == 0) ? 128 : 0;                 // lane 0: k = 128 (both stores hit P[128])
+          Pa[ka] = pa;
+          Pb[-ka] = pb;
+        } else {
+          Pa[16 * j] = pa;
+          Pb[-16 * j] = pb;
+        }
       }
       if (t == 0) {
         const float2 z0 = X16(v, 0);
         const float p = 2.0f * (z0.x + z0.y), q = 2.0f * (z0.x - z0.y);
-        Prow[0] = p * p;
-        Prow[256] = q * q;
+        Pa[0] = p * p;
+        Pb[0] = q * q;
       }
     }
     __syncthreads();
 
-    // ---- mel projection + log: lane = frame, warp = mel bins {warp, warp+8, ...} ------------
+    // ---- mel projection + log: lane = frame ---------------------------------------------------
     {
       const float* Prow = S.P + lane * kPStride;
-#pragma unroll 1
-      for (int m = warp; m < kMel; m += kWarps) {
-        const int k0 = S.bands.k0[m], n4 = S.bands.n4[m];
-        const float4* wp = S.band_w + S.bands.off4[m];
-        const float* pp = Prow + k0;
-        float acc = 0.0f;
-        for (int i = 0; i < n4; ++i) {
-          const float4 w = wp[i];
-          acc = fmaf(pp[4 * i + 0], w.x, acc);
-          acc = fmaf(pp[4 * i + 1], w.y, acc);
-          acc = fmaf(pp[4 * i + 2], w.z, acc);
-          acc = fmaf(pp[4 * i + 3], w.w, acc);
+      float* srow = stage + lane * kOutStride;
+      if (FIXED) {
+        switch (warp) {
+          case 0: mel_fixed_group<0>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          case 1: mel_fixed_group<1>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          case 2: mel_fixed_group<2>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          case 3: mel_fixed_group<3>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          case 4: mel_fixed_group<4>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          case 5: mel_fixed_group<5>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          case 6: mel_fixed_group<6>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          default: mel_fixed_group<7>(Prow, mw, srow, a.floor_, a.log_scale); break;
         }
-        stage[lane * kOutStride + m] = __log2f(fmaxf(acc, a.floor_)) * a.log_scale;
+      } else {
+#pragma unroll 1
+        for (int m = warp; m < kMel; m += kWarps) {
+          const int k0 = S.bands.k0[m], n4 = S.bands.n4[m];
+          const float4* wp = S.band_w + S.bands.off4[m];
+          const float* pp = Prow + k0;
+          float acc = 0.0f;
+          for (int i = 0; i < n4; ++i) {
+            const float4 w = wp[i];
+            acc = fmaf(pp[4 * i + 0], w.x, acc);
+            acc = fmaf(pp[4 * i + 1], w.y, acc);
+            acc = fmaf(pp[4 * i + 2], w.z, acc);
+            acc = fmaf(pp[4 * i + 3], w.w, acc);
+          }
+          srow[m] = lg2_normal(fmaxf(acc, a.floor_)) * a.log_scale;
+        }
       }
     }
     __syncthreads();
 
-    // ---- coalesced store; rows beyond n_frames[b] are the collate's 0.0 ----------------------
+    // ---- coalesced store; rows beyond n_frames[b] inside this tile are the collate's 0.0 ---------
     for (int i = tid; i < rows * (kMel / 4); i += kThreads) {
       const int r = i / (kMel / 4), m4 = (i - r * (kMel / 4)) * 4;
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -283,14 +406,6 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelArgs a)
     }
     __syncthreads();  // stage (= scratch) and wav are reused by the next tile
   }
-}
-
-__global__ void nframes_kernel(const int32_t* __restrict__ len, int32_t B, int32_t T_max, int32_t* __restrict__ n_frames) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  int n = len[b];
-  int Tb = (n >= kFrameLen) ? 1 + (n - kFrameLen) / kFrameStep : 0;
-  n_frames[b] = min(Tb, T_max);
 }
 
 }  // namespace
@@ -313,25 +428,49 @@ extern "C" int tasr_logmel_f32(const TasrFeaturizer* f, const float* wav, const 
   const int tiles_per_row = (T_max + kTileFrames - 1) / kTileFrames;
   const long long total = (long long)tiles_per_row * B;
   if (total > 0x7fffffffLL) return fail(TASR_ERR_UNSUPPORTED, "tasr_logmel_f32: too many tiles");
-  if (total == 0) {
-    nframes_kernel<<<(B + 127) / 128, 128, 0, st>>>(len, B, T_max, n_frames);
-    TASR_LAUNCH_CHECK("nframes_kernel");
-    return TASR_OK;
-  }
   static bool attr_set[64] = {false};
   const size_t smem = sizeof(Smem);
   if (dev < 64 && !attr_set[dev]) {
-    TASR_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TASR_CUDA(cudaFuncSetAttribute(logmel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TASR_CUDA(cudaFuncSetAttribute(logmel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[dev] = true;
   }
   LogmelArgs a;
   a.wav = wav; a.len = len; a.peak = peak; a.out = out; a.n_frames = n_frames;
   a.hwin = f->d_hwin; a.tw256 = f->d_tw256; a.tw512 = f->d_tw512; a.band_w = f->d_band_w; a.bands = f->d_bands;
-  a.row_stride = row_stride; a.B = B; a.T_max = T_max; a.tiles_per_row = tiles_per_row; a.total_tiles = (int)total;
+  a.row_stride = row_stride; a.B = B; a.T_max = T_max; a.tiles_per_row = tiles_per_row;
   a.normalize = f->p.normalize_signal ? 1 : 0;
   a.preemph = f->p.preemphasis; a.floor_ = f->p.output_floor; a.log_scale = f->log_scale;
-  const int grid = (int)((total < (long long)2 * sm_count()) ? total : (long long)2 * sm_count());
-  logmel_kernel<<<grid, kThreads, smem, st>>>(a);
+  // Persistent grid: two CTAs per SM; never more CTAs than work items (valid tiles + padding chunks <= total + B).
+  const long long cap = total + B;
+  const int grid = (int)((cap < (long long)2 * sm_count()) ? (cap > 0 ? cap : 1) : (long long)2 * sm_count());
+  if (f->mel_fixed) {
+    const MelFixedW* mw = reinterpret_cast<const MelFixedW*>(f->mel_fixed_w);
+    logmel_kernel<true><<<grid, kThreads, smem, st>>>(a, *mw);
+  } else {
+    static const MelFixedW zero_w = {};
+    logmel_kernel<false><<<grid, kThreads, smem, st>>>(a, zero_w);
+  }
   TASR_LAUNCH_CHECK("logmel_kernel");
   return TASR_OK;
+}
+
+// Host side of the fixed-geometry check (called by tasr_featurizer_create): fills wr/wf from the dense
+// [257,80] matrix when its sparsity structure is the compiled-in one, else returns false.
+bool tasr_mel_fixed_from_dense(const float* mel_w_host, float* wr_wf_512) {
+  MelFixedW w = {};
+  if (kMelSegStart[0] != 1 || kMelSegStart[81] != 256) return false;
+  for (int k = 0; k < kBins; ++k) {
+    int j0 = -1, j1 = -1;
+    for (int m = 0; m < kMel; ++m)
+      if (mel_w_host[k * kMel + m] != 0.0f) { if (j0 < 0) j0 = m; j1 = m; }
+    if (k == 0 || k == 256) { if (j0 >= 0) return false; continue; }
+    if (j0 < 0 || j1 - j0 > 1) return false;
+    const int seg = j0 + 1;                                  // 1..80
+    if (!(k >= kMelSegStart[seg] && k < kMelSegStart[seg + 1])) return false;
+    w.wf[k] = mel_w_host[k * kMel + j0];
+    w.wr[k] = (seg < kMel) ? mel_w_host[k * kMel + seg] : 0.0f;
+  }
+  for (int k = 0; k < 256; ++k) { wr_wf_512[k] = w.wr[k]; wr_wf_512[256 + k] = w.wf[k]; }
+  return true;
 }

@@ -364,3 +364,26 @@ def test_device_collate_unpack_bit_exact(feat, cuda_device, pcm16):
     rc = lib.tasr_unpack_f32(pb.dev_packed.data_ptr(), pb.dev_off.data_ptr(), pb.dev_len.data_ptr(), len(lens),
                              pb.n_max + 4, pb.dev_wav.data_ptr(), pb.n_max, _native.stream_ptr())
     assert rc == _native.TASR_ERR_BAD_ARG
+
+
+def test_logmel_other_filterbank_takes_generic_path(cuda_device):
+    """A filterbank other than config/model.yaml's (here 60..7600 Hz, natural log, no peak
+    normalisation, no pre-emphasis) does not have the compiled-in sparsity structure and runs the
+    generic banded projection: same tolerance against the oracle with the same parameters."""
+    cfg = dict(tasr.REFERENCE_SPEECH_CONFIG, lower_edge_hertz=60.0, upper_edge_hertz=7600.0, log_base="e",
+               normalize_signal=False, preemphasis=0.0)
+    f = tasr.SpeechFeaturizer(**cfg)
+    p = oracle.FeatParams(**cfg)
+    lens = [16000, 5281, 400, 24000]
+    wav, ln = oracle.make_waveforms(lens, seed=41, dist="tilt")
+    out, nf = run_logmel(f, wav, ln, cuda_device)
+    ref64, nref = oracle.logmel_batch_ref(wav, ln, p, dtype=np.float64)
+    np.testing.assert_array_equal(nf, nref)
+    ref32, _ = oracle.logmel_batch_ref(wav, ln, p, dtype=np.float32)
+    tol = max(LOGMEL_TOL * np.log(10.0), 4.0 * float(np.abs(ref32 - ref64).max()))   # natural log: 1e-4 * ln(10)
+    assert np.abs(out - ref64).max() <= tol
+    # and the config/model.yaml bank really is on the unrolled path
+    lib = _native.lib()
+    assert lib.tasr_featurizer_uses_fixed_mel(f._handle(cuda_device)) == 0
+    g = tasr.SpeechFeaturizer(**tasr.REFERENCE_SPEECH_CONFIG)
+    assert lib.tasr_featurizer_uses_fixed_mel(g._handle(cuda_device)) == 1
