@@ -44,12 +44,16 @@ constexpr int kScrPerFrame = 16 * kScrStride;
 constexpr int kPStride = kBins + 4;     // 261, odd; columns 257..260 stay zero (band padding of the generic path)
 constexpr int kOutStride = kMel + 1;    // 81
 constexpr int kPadChunkRows = 128;      // rows of collate padding zero-filled per work item
+constexpr int kChunkUtt = 1024;         // utterances whose work items are indexed at a time (4 per thread)
 
 struct __align__(16) Smem {
   float wav[kWavSmem];
   float2 scr[kWarps * 2 * kScrPerFrame];   // also the [32][81] output staging tile
   float P[kTileFrames * kPStride];
   float2 tw512[136];                       // W512^k, k = 0..128
+  int32_t vcum[kChunkUtt + 1];             // exclusive prefix of valid 32-frame tiles per utterance of the chunk
+  int32_t pcum[kChunkUtt + 1];             // exclusive prefix of 128-row padding chunks per utterance
+  int32_t wsum[2][kWarps];
   float4 band_w[kMelBandMaxW4];            // generic path only
   MelBands bands;                          // generic path only
 };
@@ -176,28 +180,6 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
   // ---- n_frames (src/speech_featurizer.py:163-166) -------------------------------------------
   for (int b = blockIdx.x * kThreads + tid; b < a.B; b += gridDim.x * kThreads) a.n_frames[b] = frames_of(a.len[b], a.T_max);
 
-  // ---- (b) collate padding: rows beyond the last valid tile of every utterance, 128-row chunks ----
-  {
-    int b = 0, cum = 0, cnt = -1, vt = 0;   // cnt < 0: utterance b not examined yet
-    for (int j = blockIdx.x;; j += gridDim.x) {
-      while (b < a.B) {
-        if (cnt < 0) {
-          vt = (frames_of(a.len[b], a.T_max) + kTileFrames - 1) / kTileFrames;
-          const int pad_rows = a.T_max - vt * kTileFrames;
-          cnt = pad_rows > 0 ? (pad_rows + kPadChunkRows - 1) / kPadChunkRows : 0;
-        }
-        if (j < cum + cnt) break;
-        cum += cnt; ++b; cnt = -1;
-      }
-      if (b >= a.B) break;
-      const int r0 = vt * kTileFrames + (j - cum) * kPadChunkRows;
-      const int rows = min(kPadChunkRows, a.T_max - r0);
-      float* dst = a.out + ((size_t)b * a.T_max + r0) * kMel;
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int i = tid; i < rows * (kMel / 4); i += kThreads) st_global_v4(dst + 4 * i, z);
-    }
-  }
-
   // ---- per-lane constants ----------------------------------------------------------------
   float2 hw[13];
 #pragma unroll
@@ -222,24 +204,79 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
   const float2* twp = S.tw512 + t;           // W512^(t+16j) at twp[16j]; lane t=0 uses W512^128 for j=0
   const int tw0 = (t == 0) ? 128 : 0;
 
-  // ---- (a) valid tiles, round-robin ------------------------------------------------------------
-  // `nx` runs one item ahead of `cu` so that the next tile's samples can be prefetched into L2.
-  int nb = 0, ncum = 0, ncnt = -1;      // walker state: utterance, valid tiles before it, its valid tiles
-  auto advance = [&](int jj) -> bool {  // positions (nb, ncum) on valid tile jj; false when past the end
-    while (nb < a.B) {
-      if (ncnt < 0) ncnt = (frames_of(a.len[nb], a.T_max) + kTileFrames - 1) / kTileFrames;
-      if (jj < ncum + ncnt) return true;
-      ncum += ncnt; ++nb; ncnt = -1;
+  // Work items are indexed per chunk of kChunkUtt utterances: two block-wide prefix sums (valid tiles,
+  // padding chunks) in shared memory, then item j -> (utterance, index) by binary search.  jv / jp are
+  // this CTA's next global item indices; they keep striding by gridDim.x across chunks.
+  int jv = blockIdx.x, jp = blockIdx.x, voff = 0, poff = 0;
+#pragma unroll 1
+  for (int cb = 0; cb < a.B; cb += kChunkUtt) {
+  const int nu = min(kChunkUtt, a.B - cb);
+  {
+    int vt[4], pt[4], vs = 0, ps = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int u = 4 * tid + i;
+      vt[i] = pt[i] = 0;
+      if (u < nu) {
+        vt[i] = (frames_of(a.len[cb + u], a.T_max) + kTileFrames - 1) / kTileFrames;
+        const int pad_rows = a.T_max - vt[i] * kTileFrames;
+        pt[i] = pad_rows > 0 ? (pad_rows + kPadChunkRows - 1) / kPadChunkRows : 0;
+      }
+      vs += vt[i]; ps += pt[i];
     }
-    return false;
+    int vi = vs, pi = ps;   // inclusive scan over the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v2 = __shfl_up_sync(0xffffffffu, vi, d), p2 = __shfl_up_sync(0xffffffffu, pi, d);
+      if (lane >= d) { vi += v2; pi += p2; }
+    }
+    if (lane == 31) { S.wsum[0][warp] = vi; S.wsum[1][warp] = pi; }
+    __syncthreads();
+    int vb = vi - vs, pb = pi - ps;
+    for (int w = 0; w < warp; ++w) { vb += S.wsum[0][w]; pb += S.wsum[1][w]; }
+    if (tid == 0) { S.vcum[0] = 0; S.pcum[0] = 0; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      vb += vt[i]; pb += pt[i];
+      S.vcum[4 * tid + i + 1] = vb;
+      S.pcum[4 * tid + i + 1] = pb;
+    }
+    __syncthreads();
+  }
+  const int vtot = S.vcum[nu], ptot = S.pcum[nu];
+  auto find = [&](const int32_t* cum, int x) -> int {   // largest u in [0,nu) with cum[u] <= x
+    int lo = 0, hi = nu;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (cum[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
   };
-  int j = blockIdx.x;
-  bool more = advance(j);
-  while (more) {
-    const int b = nb;
-    const int tf = j - ncum;
-    j += gridDim.x;
-    more = advance(j);
+
+  // ---- (b) collate padding: rows beyond the last valid tile of every utterance, 128-row chunks ----
+  for (; jp < poff + ptot; jp += gridDim.x) {
+    const int u = find(S.pcum, jp - poff);
+    const int vt = S.vcum[u + 1] - S.vcum[u];
+    const int r0 = vt * kTileFrames + (jp - poff - S.pcum[u]) * kPadChunkRows;
+    const int rows = min(kPadChunkRows, a.T_max - r0);
+    float* dst = a.out + ((size_t)(cb + u) * a.T_max + r0) * kMel;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < rows * (kMel / 4); i += kThreads) st_global_v4(dst + 4 * i, z);
+  }
+
+  // ---- (a) valid tiles, round-robin ------------------------------------------------------------
+#pragma unroll 1
+  for (; jv < voff + vtot; jv += gridDim.x) {
+    const int u = find(S.vcum, jv - voff);
+    const int b = cb + u;
+    const int tf = jv - voff - S.vcum[u];
+
+    if (jv + (int)gridDim.x < voff + vtot && tid < 168) {  // next tile -> L2: 5360 samples = 167.5 lines of 128 B
+      const int un = find(S.vcum, jv + gridDim.x - voff);
+      const float* nrow = a.wav + (size_t)(cb + un) * a.row_stride;
+      const int ns = (jv + (int)gridDim.x - voff - S.vcum[un]) * kTileFrames * kFrameStep + tid * 32;
+      if (ns < a.len[cb + un]) prefetch_l2(nrow + ns);
+    }
 
     const int n = a.len[b];
     const int Tb = frames_of(n, a.T_max);
@@ -247,12 +284,6 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
     const int rows = min(kTileFrames, a.T_max - f0);
     const int nvalid = min(kTileFrames, Tb - f0);   // >= 1: only valid tiles are enumerated
     float* orow = a.out + ((size_t)b * a.T_max + f0) * kMel;
-
-    if (more && tid < 168) {  // next tile: 5360 samples = 167.5 lines of 128 B
-      const float* nrow = a.wav + (size_t)nb * a.row_stride;
-      const int ns = (j - ncum) * kTileFrames * kFrameStep + tid * 32;
-      if (ns < a.len[nb]) prefetch_l2(nrow + ns);
-    }
 
     // ---- stage the tile: gain, pre-emphasis (reference float32 op order), to shared --------
     {
@@ -405,6 +436,9 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
       st_global_v4(orow + 4 * i, o);
     }
     __syncthreads();  // stage (= scratch) and wav are reused by the next tile
+  }
+  voff += vtot; poff += ptot;
+  __syncthreads();   // the prefix tables are rebuilt for the next chunk
   }
 }
 

@@ -387,3 +387,19 @@ def test_logmel_other_filterbank_takes_generic_path(cuda_device):
     assert lib.tasr_featurizer_uses_fixed_mel(f._handle(cuda_device)) == 0
     g = tasr.SpeechFeaturizer(**tasr.REFERENCE_SPEECH_CONFIG)
     assert lib.tasr_featurizer_uses_fixed_mel(g._handle(cuda_device)) == 1
+
+
+def test_logmel_many_short_utterances_cross_index_chunks(feat, cuda_device):
+    """More utterances than one work-index chunk of the kernel (1024): 2500 utterances of 0..3 frames
+    plus a few long ones; frame counts bit-exact, values against the float32 oracle, padding zero."""
+    rng = np.random.default_rng(5)
+    lens = rng.integers(0, 900, size=2500).astype(np.int32)
+    lens[[7, 1023, 1024, 2047, 2499]] = [16000, 5281, 8000, 400, 12000]
+    wav, ln = oracle.make_waveforms(lens, seed=43, dist="tilt")
+    out, nf = run_logmel(feat, wav, ln, cuda_device)
+    ref64, nref = oracle.logmel_batch_ref(wav, ln, dtype=np.float64)
+    np.testing.assert_array_equal(nf, nref)
+    assert out.shape == ref64.shape
+    assert np.abs(out - ref64).max() <= band_tol(wav, ln, ref64)
+    for b in (0, 7, 1023, 1024, 1500, 2047, 2499):
+        assert not out[b, nf[b]:].any()
