@@ -135,6 +135,22 @@ int tasr_sepconv_plan_destroy(TasrSepConvPlan* plan);
 int tasr_sepconv1d_tf32(const TasrSepConvPlan* plan, const float* x, int32_t batch, int32_t t_in,
                         float* y, int32_t t_out, tasr_stream_t stream);
 
+/* Ragged form of the same layer for zero-padded batches (src/dataset.py:236-252 pads with 0.0 and the
+ * reference then convolves the padding too, encoder.py:60 — far from the data that just reproduces one
+ * constant row per layer).  tasr_sepconv_plan_set_pad_row tells the plan what every padding row of its
+ * INPUT looks like (device [c_in]; NULL = all zeros, i.e. the collate's padding) and computes, with the
+ * layer's own arithmetic, the row it produces from a receptive field made of that row;
+ * tasr_sepconv_plan_pad_row returns it (device [c_out]) so the next layer's plan can be chained.
+ * tasr_sepconv1d_tf32_ragged then takes len0 [batch] (device int32) and shift: rows
+ * t >= ceil(len0[b] / 2^shift) of x[b] must all equal that padding row (len0 = n_frames of the features,
+ * shift = index of the layer in the stride-2 stack).  Tiles whose receptive field lies entirely there are
+ * filled with the constant row instead of being computed; every value of y — valid and padded — is
+ * bit-identical to what tasr_sepconv1d_tf32 writes for the same input. */
+int tasr_sepconv_plan_set_pad_row(TasrSepConvPlan* plan, const float* pad_row_in, tasr_stream_t stream);
+const float* tasr_sepconv_plan_pad_row(const TasrSepConvPlan* plan);
+int tasr_sepconv1d_tf32_ragged(const TasrSepConvPlan* plan, const float* x, const int32_t* len0, int32_t shift,
+                               int32_t batch, int32_t t_in, float* y, int32_t t_out, tasr_stream_t stream);
+
 /* Replaces math_util.get_conv_length applied per layer (src/utils/math_util.py:20-32,
  * encoder.py:60-68) and lengths_to_padding_mask (encoder.py:43-48).
  * len_out [n_layers, batch] int32 gets the length after every layer, computed exactly as the

@@ -49,6 +49,9 @@ _SIGNATURES = {
     "tasr_sepconv_plan_create": (C.c_int, [C.POINTER(TasrSepConvLayer), C.POINTER(_vp), _vp]),
     "tasr_sepconv_plan_destroy": (C.c_int, [_vp]),
     "tasr_sepconv1d_tf32": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _vp]),
+    "tasr_sepconv_plan_set_pad_row": (C.c_int, [_vp, _vp, _vp]),
+    "tasr_sepconv_plan_pad_row": (C.c_void_p, [_vp]),
+    "tasr_sepconv1d_tf32_ragged": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp]),
     "tasr_conv_lengths_mask": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32),
                                          C.POINTER(_i32), _vp, _vp, _i32, _vp]),
     "tasr_count_nonzero_frames": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),

@@ -54,6 +54,7 @@ struct __align__(16) Smem {
   int32_t vcum[kChunkUtt + 1];             // exclusive prefix of valid 32-frame tiles per utterance of the chunk
   int32_t pcum[kChunkUtt + 1];             // exclusive prefix of 128-row padding chunks per utterance
   int32_t wsum[2][kWarps];
+  int2 list[kThreads];                     // this CTA's next valid tiles: (utterance within chunk, tile index)
   float4 band_w[kMelBandMaxW4];            // generic path only
   MelBands bands;                          // generic path only
 };
@@ -265,17 +266,28 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
   }
 
   // ---- (a) valid tiles, round-robin ------------------------------------------------------------
+  // This CTA's tiles of the chunk are jv, jv+grid, ...; they are located once, one per thread, into a
+  // shared list (utterance, tile index) that the tile loop then just reads.
 #pragma unroll 1
-  for (; jv < voff + vtot; jv += gridDim.x) {
-    const int u = find(S.vcum, jv - voff);
-    const int b = cb + u;
-    const int tf = jv - voff - S.vcum[u];
+  while (jv < voff + vtot) {
+  const int nlist = min(kThreads, (voff + vtot - jv + (int)gridDim.x - 1) / (int)gridDim.x);
+  if (tid < nlist) {
+    const int x = jv - voff + tid * (int)gridDim.x;
+    const int u = find(S.vcum, x);
+    S.list[tid] = make_int2(u, x - S.vcum[u]);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int li = 0; li < nlist; ++li) {
+    const int2 item = S.list[li];
+    const int b = cb + item.x;
+    const int tf = item.y;
 
-    if (jv + (int)gridDim.x < voff + vtot && tid < 168) {  // next tile -> L2: 5360 samples = 167.5 lines of 128 B
-      const int un = find(S.vcum, jv + gridDim.x - voff);
-      const float* nrow = a.wav + (size_t)(cb + un) * a.row_stride;
-      const int ns = (jv + (int)gridDim.x - voff - S.vcum[un]) * kTileFrames * kFrameStep + tid * 32;
-      if (ns < a.len[cb + un]) prefetch_l2(nrow + ns);
+    if (li + 1 < nlist && tid < 168) {  // next tile -> L2: 5360 samples = 167.5 lines of 128 B
+      const int2 nxt = S.list[li + 1];
+      const float* nrow = a.wav + (size_t)(cb + nxt.x) * a.row_stride;
+      const int ns = nxt.y * kTileFrames * kFrameStep + tid * 32;
+      if (ns < a.len[cb + nxt.x]) prefetch_l2(nrow + ns);
     }
 
     const int n = a.len[b];
@@ -436,6 +448,8 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
       st_global_v4(orow + 4 * i, o);
     }
     __syncthreads();  // stage (= scratch) and wav are reused by the next tile
+  }
+  jv += nlist * (int)gridDim.x;   // (the tile loop ends on a barrier, so the list can be rewritten)
   }
   voff += vtot; poff += ptot;
   __syncthreads();   // the prefix tables are rebuilt for the next chunk

@@ -34,6 +34,9 @@ struct TasrSepConvPlan {
   int n_chunks;         // ceil(c_in / 32)
   float* d_bpack;       // [n_split][n_chunks][NT*32] shared-memory images of pw^T
   void* kernel;         // template instance for (c_in, activation)
+  float* d_pad_in;      // [9][c_in]  nine copies of the input's padding row (ragged mode)
+  float* d_pad_out;     // [c_out]    this layer's output for an all-padding receptive field
+  int pad_ready;
 };
 
 namespace {
@@ -175,6 +178,11 @@ struct SepArgs {
   const float* bias;
   float* y;
   int32_t T_in, T_out, C_in, C_out, NT, n_chunks, act;
+  // ragged mode (len0 != nullptr): rows t >= ceil(len0[b] / 2^shift) of x[b] all equal the padding row the
+  // plan was given, so a tile whose receptive field starts there is the constant row pad_out: filled, not computed.
+  const int32_t* len0;
+  const float* pad_out;
+  int32_t shift;
 };
 
 // CIN > 0 bakes the row stride into load immediates (the reference shapes 80/192/384 and the
@@ -197,6 +205,20 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
   const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), bar_u = smem_u32(bars);
 
   const int b = blockIdx.z, nh = blockIdx.y, t0 = blockIdx.x * kMT, n0 = nh * NT;
+
+  if (a.len0 != nullptr) {               // CTA-uniform: leaves before any barrier / TMEM allocation
+    const int cf = (max(a.len0[b], 0) + (1 << a.shift) - 1) >> a.shift;
+    if (2 * t0 >= cf) {
+      const int rows = min(kMT, a.T_out - t0), q4 = NT >> 2;
+      float* dst = a.y + ((size_t)b * a.T_out + t0) * a.C_out + n0;
+      const float4* pr = reinterpret_cast<const float4*>(a.pad_out + n0);
+      for (int i = tid; i < rows * q4; i += kThreads) {
+        const int r = i / q4, c4 = i - r * q4;
+        *reinterpret_cast<float4*>(dst + (size_t)r * a.C_out + 4 * c4) = __ldg(pr + c4);
+      }
+      return;
+    }
+  }
 
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   if (tid == 32) {
@@ -381,7 +403,12 @@ extern "C" int tasr_sepconv_plan_create(const TasrSepConvLayer* L, TasrSepConvPl
   p->NT = L->c_out / n_split;
   p->n_chunks = (L->c_in + kKC - 1) / kKC;
   p->d_bpack = nullptr;
+  p->d_pad_in = nullptr;
+  p->d_pad_out = nullptr;
+  p->pad_ready = 0;
   int rc = check_cuda(cudaGetDevice(&p->device), "cudaGetDevice");
+  if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_pad_in, (size_t)9 * L->c_in * sizeof(float)), "cudaMalloc pad rows");
+  if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_pad_out, (size_t)L->c_out * sizeof(float)), "cudaMalloc pad row");
   const size_t n = (size_t)n_split * p->n_chunks * p->NT * kKC;
   if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_bpack, n * sizeof(float)), "cudaMalloc packed pointwise weights");
   if (rc == TASR_OK) {
@@ -403,25 +430,62 @@ extern "C" int tasr_sepconv_plan_create(const TasrSepConvLayer* L, TasrSepConvPl
 extern "C" int tasr_sepconv_plan_destroy(TasrSepConvPlan* p) {
   if (!p) return TASR_OK;
   cudaFree(p->d_bpack);
+  cudaFree(p->d_pad_in);
+  cudaFree(p->d_pad_out);
   delete p;
   return TASR_OK;
 }
 
-extern "C" int tasr_sepconv1d_tf32(const TasrSepConvPlan* p, const float* x, int32_t B, int32_t T_in,
-                                   float* y, int32_t T_out, tasr_stream_t stream) {
-  if (!p) return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32: null plan");
-  int rc = validate_sepconv("tasr_sepconv1d_tf32", x, B, T_in, &p->L, y, T_out);
+static int launch_tf32(const char* who, const TasrSepConvPlan* p, const float* x, const int32_t* len0, int32_t shift,
+                       int32_t B, int32_t T_in, float* y, int32_t T_out, tasr_stream_t stream) {
+  if (!p) return fail(TASR_ERR_BAD_ARG, "%s: null plan", who);
+  int rc = validate_sepconv(who, x, B, T_in, &p->L, y, T_out);
   if (rc != TASR_OK) return rc;
   int dev = 0;
   TASR_CUDA(cudaGetDevice(&dev));
-  if (dev != p->device) return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32: plan was created on device %d, current device is %d", p->device, dev);
+  if (dev != p->device) return fail(TASR_ERR_BAD_ARG, "%s: plan was created on device %d, current device is %d", who, p->device, dev);
   if (B == 0 || T_out == 0) return TASR_OK;
   SepArgs a;
   a.x = x; a.dw = p->L.dw; a.bpack = p->d_bpack; a.bias = p->L.bias; a.y = y;
   a.T_in = T_in; a.T_out = T_out; a.C_in = p->L.c_in; a.C_out = p->L.c_out; a.NT = p->NT;
   a.n_chunks = p->n_chunks; a.act = p->L.activation;
+  a.len0 = len0; a.pad_out = p->d_pad_out; a.shift = shift;
   dim3 grid((T_out + kMT - 1) / kMT, p->n_split, B);
   reinterpret_cast<SepKernel>(p->kernel)<<<grid, kThreads, smem_bytes(p->NT), (cudaStream_t)stream>>>(a);
   TASR_LAUNCH_CHECK("sepconv_tf32_kernel");
   return TASR_OK;
+}
+
+extern "C" int tasr_sepconv1d_tf32(const TasrSepConvPlan* p, const float* x, int32_t B, int32_t T_in,
+                                   float* y, int32_t T_out, tasr_stream_t stream) {
+  return launch_tf32("tasr_sepconv1d_tf32", p, x, nullptr, 0, B, T_in, y, T_out, stream);
+}
+
+extern "C" int tasr_sepconv_plan_set_pad_row(TasrSepConvPlan* p, const float* pad_row_in, tasr_stream_t stream) {
+  if (!p) return fail(TASR_ERR_BAD_ARG, "tasr_sepconv_plan_set_pad_row: null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t row = (size_t)p->L.c_in * sizeof(float);
+  if (pad_row_in) {
+    for (int k = 0; k < 9; ++k)
+      TASR_CUDA(cudaMemcpyAsync(p->d_pad_in + (size_t)k * p->L.c_in, pad_row_in, row, cudaMemcpyDeviceToDevice, st));
+  } else {
+    TASR_CUDA(cudaMemsetAsync(p->d_pad_in, 0, 9 * row, st));
+  }
+  // The padding row of the output is whatever THIS kernel computes for a receptive field made of the
+  // input's padding row (one output frame from nine identical rows), so filled and computed rows are
+  // bit-identical and the constant propagates exactly through the stack.
+  int rc = launch_tf32("tasr_sepconv_plan_set_pad_row", p, p->d_pad_in, nullptr, 0, 1, 9, p->d_pad_out, 1, stream);
+  if (rc == TASR_OK) p->pad_ready = 1;
+  return rc;
+}
+
+extern "C" const float* tasr_sepconv_plan_pad_row(const TasrSepConvPlan* p) { return (p && p->pad_ready) ? p->d_pad_out : nullptr; }
+
+extern "C" int tasr_sepconv1d_tf32_ragged(const TasrSepConvPlan* p, const float* x, const int32_t* len0, int32_t shift,
+                                          int32_t B, int32_t T_in, float* y, int32_t T_out, tasr_stream_t stream) {
+  if (!p || !len0) return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32_ragged: null argument");
+  if (shift < 0 || shift > 30) return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32_ragged: shift must be in [0,30]");
+  if (!p->pad_ready)
+    return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32_ragged: call tasr_sepconv_plan_set_pad_row first (the input's padding row is unknown)");
+  return launch_tf32("tasr_sepconv1d_tf32_ragged", p, x, len0, shift, B, T_in, y, T_out, stream);
 }
