@@ -206,8 +206,10 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
 
   const int b = blockIdx.z, nh = blockIdx.y, t0 = blockIdx.x * kMT, n0 = nh * NT;
 
+  // Rows t with 2t >= cf have a receptive field made of the input's padding row only.
+  int cf = 0x7fffffff;
   if (a.len0 != nullptr) {               // CTA-uniform: leaves before any barrier / TMEM allocation
-    const int cf = (max(a.len0[b], 0) + (1 << a.shift) - 1) >> a.shift;
+    cf = (max(a.len0[b], 0) + (1 << a.shift) - 1) >> a.shift;
     if (2 * t0 >= cf) {
       const int rows = min(kMT, a.T_out - t0), q4 = NT >> 2;
       float* dst = a.y + ((size_t)b * a.T_out + t0) * a.C_out + n0;
@@ -237,6 +239,10 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
   const int r0 = 2 * tw;                 // first input row of the run
   const float* xrow = a.x + ((size_t)b * a.T_in + r0) * C_in + lane;
   const bool run_inside = (r0 + kWin <= a.T_in);   // warp-uniform: no row of this run is past the input
+  // Ragged mode: a run that starts in the padding produces only the constant row; its depthwise work is
+  // skipped (its A rows stay stale — every output row depends on its own A row only) and the epilogue
+  // writes the constant row for those frames.
+  const bool run_needed = (r0 < cf);
 
   for (int kc = 0; kc < a.n_chunks; ++kc) {
     const int s = kc & 1, use = kc >> 1;
@@ -252,6 +258,7 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
     const int c0 = kc * kKC;
     const int kvalid = min(kKC, C_in - c0);
     const bool cok = lane < kvalid;
+    if (run_needed) {
     float v[kWin];
     float w[9];
     if (run_inside && kvalid == kKC) {   // common case: unpredicated loads at immediate offsets
@@ -276,6 +283,7 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
       const int row = warp * kRun + j;
       const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u;
       *reinterpret_cast<uint32_t*>(As + off) = to_tf32(acc);
+    }
     }
     fence_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
     __syncthreads();
@@ -318,8 +326,9 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
       for (int i = 0; i < 8; ++i) {
         const int rr = (lane >> 3) + 4 * i;
         const int c4 = (lane & 7) * 4;
-        const float4 o = *reinterpret_cast<const float4*>(stg + rr * kStgStride + c4);
+        float4 o = *reinterpret_cast<const float4*>(stg + rr * kStgStride + c4);
         const int t = t0 + q * 32 + rr;
+        if (2 * t >= cf) o = __ldg(reinterpret_cast<const float4*>(a.pad_out + n0 + g * 32 + c4));
         if (t < a.T_out)
           *reinterpret_cast<float4*>(a.y + ((size_t)b * a.T_out + t) * a.C_out + n0 + g * 32 + c4) = o;
       }

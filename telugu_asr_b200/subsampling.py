@@ -41,7 +41,8 @@ def get_conv_length(input_length: int, kernel_size: int, padding: str, strides: 
 class Conv1DSubsamplingLayer:
     def __init__(self, model_dim: int = 288, subsampling_config: dict | None = None,
                  kernel_regularizer=None, bias_regularizer=None, name: str = "conv1d_subsampling",
-                 input_dim: int = 80, math: str = "tf32", seed: int | None = None, **kwargs):
+                 input_dim: int = 80, math: str = "tf32", seed: int | None = None,
+                 assume_zero_padding: bool = True, **kwargs):
         subsampling_config = subsampling_config or {}
         self.name = name
         self.filters = [model_dim, 2 * model_dim, model_dim]                        # encoder.py:21
@@ -58,6 +59,10 @@ class Conv1DSubsamplingLayer:
         if math not in ("fp32", "tf32"):
             raise ValueError("math must be 'fp32' or 'tf32'")
         self.math = math
+        # ragged mode (TF32 path, when lengths are known): rows t >= lengths[b] of the input are taken to be
+        # the collate's 0.0 padding (src/dataset.py:241), so tiles deep inside the padding are filled with the
+        # constant row the convolution produces there instead of being computed.  Same values everywhere.
+        self.assume_zero_padding = bool(assume_zero_padding)
         self.input_dim = input_dim
         self._seed = seed
         self.weights: list[tuple[torch.Tensor, torch.Tensor, torch.Tensor]] | None = None  # per layer (dw, pw, bias)
@@ -139,6 +144,11 @@ class Conv1DSubsamplingLayer:
                 out = C.c_void_p()
                 _native.check(L.tasr_sepconv_plan_create(C.byref(ls), C.byref(out), st))
                 plans.append(out.value)
+            # chain the padding rows: zeros into layer 1, each layer's constant output row into the next
+            prev = None
+            for pl in plans:
+                _native.check(L.tasr_sepconv_plan_set_pad_row(pl, prev, st))
+                prev = L.tasr_sepconv_plan_pad_row(pl)
         self._plans = plans
 
     # ------------------------------------------------------------------ reference API
@@ -232,6 +242,7 @@ class Conv1DSubsamplingLayer:
         L = _native.lib()
 
         lengths = None
+        prefix_lengths = mask is not None and mask.dim() == 1   # explicit frame counts: padding is a zero suffix
         if mask is not None:
             _native.require_cuda(mask, "mask")
             if mask.dim() == 1:                      # additive: frame counts straight from the featurizer
@@ -258,7 +269,10 @@ class Conv1DSubsamplingLayer:
                 cout = self.filters[i]
                 y = torch.empty((B, t_out, cout), dtype=torch.float32, device=x.device)
                 if B and t_out:
-                    if use_tf32:
+                    if use_tf32 and prefix_lengths and self.assume_zero_padding:
+                        _native.check(L.tasr_sepconv1d_tf32_ragged(self._plans[i], h.data_ptr(), lengths.data_ptr(), i,
+                                                                   B, t_in, y.data_ptr(), t_out, st))
+                    elif use_tf32:
                         _native.check(L.tasr_sepconv1d_tf32(self._plans[i], h.data_ptr(), B, t_in, y.data_ptr(), t_out, st))
                     else:
                         ls = self._layer_struct(i)

@@ -403,3 +403,36 @@ def test_logmel_many_short_utterances_cross_index_chunks(feat, cuda_device):
     assert np.abs(out - ref64).max() <= band_tol(wav, ln, ref64)
     for b in (0, 7, 1023, 1024, 1500, 2047, 2499):
         assert not out[b, nf[b]:].any()
+
+
+def test_subsampling_ragged_fill_is_bit_identical_to_dense(cuda_device):
+    """Ragged mode fills tiles that lie deep in the collate padding with the layer's constant padding row
+    instead of computing them: every value of the output, valid and padded, must equal the dense run."""
+    from telugu_asr_b200.synth import draw_lengths
+    lens = draw_lengths(24, 1600, 240000, seed=9)
+    lens[1], lens[2], lens[3] = 399, 240000, 16000
+    wav, ln = oracle.make_waveforms(lens, seed=9, dist="tilt")
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    feat = tasr.SpeechFeaturizer(**tasr.REFERENCE_SPEECH_CONFIG)
+    feats, nf = feat(gpu(wav, cuda_device), gpu(ln, cuda_device))
+    outs = {}
+    for ragged in (False, True):
+        layer = tasr.Conv1DSubsamplingLayer(192, tasr.REFERENCE_SUBSAMPLING_CONFIG, math="tf32", assume_zero_padding=ragged)
+        layer.set_weights(weights, cuda_device)
+        outs[ragged] = _call_or_skip(layer, feats, mask=nf, return_lengths=True)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[True][0], outs[False][0])
+    assert torch.equal(outs[True][1], outs[False][1]) and torch.equal(outs[True][2], outs[False][2])
+    # and against the oracle at every position (padded positions are conv-over-zero-padding values)
+    ref_out, ref_mask, ref_len = oracle.subsample_ref(feats.cpu().numpy(), nf.cpu().numpy(), weights, dtype=np.float32)
+    o = outs[True][0].cpu().numpy()
+    assert np.abs(o - ref_out).max() / np.abs(ref_out).max() <= SUB_TOL_TF32
+    # the raw entry point refuses ragged calls on a plan without a padding row
+    lib = _native.lib()
+    ls = layer._layer_struct(0)
+    pl = ctypes.c_void_p()
+    _native.check(lib.tasr_sepconv_plan_create(ctypes.byref(ls), ctypes.byref(pl), _native.stream_ptr()))
+    y = torch.empty((24, 745, 192), device=cuda_device)
+    rc = lib.tasr_sepconv1d_tf32_ragged(pl, feats.data_ptr(), nf.data_ptr(), 0, 24, 1498, y.data_ptr(), 745, _native.stream_ptr())
+    assert rc == _native.TASR_ERR_BAD_ARG and b"set_pad_row" in lib.tasr_last_error()
+    lib.tasr_sepconv_plan_destroy(pl)

@@ -37,7 +37,9 @@ for i in range(3):
     t_out = (t_in - 9) // 2 + 1
     y = torch.empty((256, t_out, sub.filters[i]), dtype=torch.float32, device=dev)
     st = _native.stream_ptr()
-    if math == "tf32":
+    if math == "tf32" and "dense" not in sys.argv:
+        f = lambda h=h, y=y, t_in=t_in, t_out=t_out, i=i: _native.check(L.tasr_sepconv1d_tf32_ragged(sub._plans[i], h.data_ptr(), nf.data_ptr(), i, 256, t_in, y.data_ptr(), t_out, st))
+    elif math == "tf32":
         f = lambda h=h, y=y, t_in=t_in, t_out=t_out, i=i: _native.check(L.tasr_sepconv1d_tf32(sub._plans[i], h.data_ptr(), 256, t_in, y.data_ptr(), t_out, st))
     else:
         ls = sub._layer_struct(i)
