@@ -127,3 +127,18 @@ def require_cuda(t, name: str):
 def stream_ptr() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+# ---- optional per-stage CUDA-event marks (bench.py / tools): off unless `stage_marks` is a list ----------
+stage_marks: list | None = None
+
+
+def mark(name: str) -> None:
+    """Record a CUDA event on the current stream under `name` when stage timing is switched on
+    (`_native.stage_marks = []`); a no-op otherwise.  Consecutive marks bracket one stage."""
+    if stage_marks is None:
+        return
+    import torch
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    stage_marks.append((name, ev))

@@ -211,12 +211,15 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
   if (a.len0 != nullptr) {               // CTA-uniform: leaves before any barrier / TMEM allocation
     cf = (max(a.len0[b], 0) + (1 << a.shift) - 1) >> a.shift;
     if (2 * t0 >= cf) {
-      const int rows = min(kMT, a.T_out - t0), q4 = NT >> 2;
+      const int rows = min(kMT, a.T_out - t0), q4 = NT >> 2;   // q4 <= 64 float4 per row: one warp per row
       float* dst = a.y + ((size_t)b * a.T_out + t0) * a.C_out + n0;
       const float4* pr = reinterpret_cast<const float4*>(a.pad_out + n0);
-      for (int i = tid; i < rows * q4; i += kThreads) {
-        const int r = i / q4, c4 = i - r * q4;
-        *reinterpret_cast<float4*>(dst + (size_t)r * a.C_out + 4 * c4) = __ldg(pr + c4);
+      const float4 p0 = (lane < q4) ? __ldg(pr + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 p1 = (lane + 32 < q4) ? __ldg(pr + lane + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = warp; r < rows; r += kThreads / 32) {
+        float4* row = reinterpret_cast<float4*>(dst + (size_t)r * a.C_out);
+        if (lane < q4) row[lane] = p0;
+        if (lane + 32 < q4) row[lane + 32] = p1;
       }
       return;
     }

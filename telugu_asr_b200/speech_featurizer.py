@@ -228,10 +228,12 @@ class SpeechFeaturizer:
         with torch.cuda.device(dev):
             st = _native.stream_ptr()
             peak_ptr = None
+            _native.mark("begin")
             if self._normalize_signal:
                 peak = torch.empty((B,), dtype=torch.float32, device=dev)
                 _native.check(L.tasr_absmax_f32(wav.data_ptr(), lengths.data_ptr(), B, row_stride, peak.data_ptr(), st))
                 peak_ptr = peak.data_ptr()
+                _native.mark("absmax_kernel")
             ev = self.profile_events
             if ev is not None:   # bench.py: CUDA events around the dominant kernel, on its own stream
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -241,4 +243,5 @@ class SpeechFeaturizer:
             if ev is not None:
                 e1.record()
                 ev.append((e0, e1))
+            _native.mark("logmel_kernel")
         return out, n_frames

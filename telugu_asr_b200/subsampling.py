@@ -277,10 +277,12 @@ class Conv1DSubsamplingLayer:
                     else:
                         ls = self._layer_struct(i)
                         _native.check(L.tasr_sepconv1d_f32(h.data_ptr(), B, t_in, C.byref(ls), y.data_ptr(), t_out, st))
+                _native.mark(f"sepconv_layer{i + 1}")
                 h, t_in = y, t_out
         padding_mask, len_all = None, None
         if lengths is not None:
             len_all, padding_mask = self.conv_lengths(lengths, with_mask=True, max_frames=max_frames)
+            _native.mark("lengths_mask")
         if return_lengths:
             return h, padding_mask, len_all
         return h, padding_mask

@@ -1,0 +1,103 @@
+"""Turn one tools/gpu_cycle.sh capture (gpurun_out/*_TAG.*) into the tracked evidence under profiles/:
+  profiles/<name>_launches.csv   the ncu per-launch list of one bench run (cold-cache, serialised)
+  profiles/<name>_summary.md     step table (share per kernel), --set full table, the bench line
+  profiles/traffic.json          dram bytes per launch per kernel (bench.py reads roofline.traffic here)
+Usage: python tools/make_profile_summary.py TAG NAME "commit / description line"
+"""
+import csv
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag, name, desc = sys.argv[1], sys.argv[2], sys.argv[3]
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+
+
+def short(k):
+    k = k.replace("<unnamed>::", "").replace("void ", "")
+    return k.split("(")[0]
+
+
+# ---- launch list --------------------------------------------------------------------------------
+src = os.path.join(G, f"launches_{tag}.csv")
+shutil.copy(src, os.path.join(P, f"{name}_launches.csv"))
+rows = list(csv.DictReader(l for l in open(src) if l.startswith('"')))
+launches = [(short(r["Kernel Name"]), r["Grid Size"], r["Block Size"], float(r["Metric Value"]) / 1e3) for r in rows]
+# one timed step = from the 4th absmax launch (3 warm-up steps) to the next absmax
+idx = [i for i, l in enumerate(launches) if l[0] == "absmax_kernel"]
+step = launches[idx[3]:idx[4]]
+total = sum(l[3] for l in step)
+
+# ---- --set full -----------------------------------------------------------------------------------
+rep = os.path.join(G, f"prof_{tag}.ncu-rep")
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+r = list(csv.reader(out.splitlines()))
+h = r[0]
+col = {n: i for i, n in enumerate(h)}
+want = [("time us", "gpu__time_duration.sum"), ("dram rd MB", "dram__bytes_read.sum"), ("dram wr MB", "dram__bytes_write.sum"),
+        ("DRAM %", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), ("SM %", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+        ("issue %", "smsp__issue_active.avg.pct_of_peak_sustained_active"), ("FMA pipe %", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+        ("tensor %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"), ("warp inst M", "smsp__inst_executed.sum"),
+        ("regs", "launch__registers_per_thread"), ("warps act %", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+        ("smem KB", "launch__shared_mem_per_block_dynamic")]
+full = []
+traffic = {}
+for row in r[2:]:
+    k = short(row[col["Kernel Name"]])
+    if "sepconv" in k:
+        k = row[col["Kernel Name"]].replace("<unnamed>::", "").replace("void ", "").split("(")[0]
+    vals = {}
+    for label, m in want:
+        v = row[col[m]].replace(",", "") if m in col else ""
+        u = r[1][col[m]] if m in col else ""
+        try:
+            f = float(v)
+            if m == "smsp__inst_executed.sum":
+                f /= 1e6
+            if u == "ns":
+                f /= 1e3
+            if u == "byte":
+                f /= 1e6
+            if u == "Kbyte" and "bytes" in m:
+                f /= 1e3
+            if u == "Gbyte":
+                f *= 1e3
+            vals[label] = f
+        except ValueError:
+            vals[label] = v
+    full.append((k, vals))
+    traffic[k] = {"dram_bytes_per_launch": int((vals["dram rd MB"] + vals["dram wr MB"]) * 1e6), "ncu_time_us": vals["time us"]}
+
+bench_line = open(os.path.join(G, f"bench_{tag}.log")).read().strip().splitlines()[-1]
+bj = json.loads(bench_line)
+
+with open(os.path.join(P, f"{name}_summary.md"), "w") as fh:
+    fh.write(f"# {name} — {desc}\n\n")
+    fh.write("Commands (1 x B200 under `gpurun`, `tools/gpu_cycle.sh`): `python bench.py` (plain, the bench line below), then\n"
+             "`python bench.py --steps 3 --warmup 3 --no-cpu-baseline` plain (exit 0) and the same under\n"
+             "`ncu --metrics gpu__time_duration.sum --clock-control none` (launch list) and\n"
+             "`ncu --set full --clock-control none --import-source on -k regex:logmel_kernel|sepconv_tf32|absmax -s 15 -c 5`\n"
+             "(the five kernels of the first timed step).  ncu per-launch times are cold-cache and serialised: compare shares.\n\n")
+    fh.write(f"Bench line (not under ncu): **{bj['value']:.0f} audio-s/s**, {bj['ms_per_step'] * 1e3:.1f} us/step; "
+             f"e2e {bj['e2e']['value']:.0f} audio-s/s ({bj['e2e']['ms_per_step']:.3f} ms/step, H2D {bj['e2e']['h2d_bytes_per_step'] / 1e6:.1f} MB, "
+             f"D2H {bj['e2e']['d2h_bytes_per_step'] / 1e6:.1f} MB); roofline {bj['roofline']['kernel']} "
+             f"{bj['roofline']['achieved']:.0f} GB/s = {bj['roofline']['frac']:.3f} of measured {bj['roofline']['peak']:.0f} GB/s; "
+             f"CPU baseline {bj.get('cpu_baseline', {}).get('value', 0):.0f} audio-s/s on {bj.get('cpu_baseline', {}).get('cores')} cores.\n\n")
+    fh.write("CUDA-event stage times inside bench.py (median of 20 steps, us): "
+             + ", ".join(f"{k} {v['us']}" for k, v in bj.get("stages", {}).items()) + "\n\n")
+    fh.write("## Launch list: one timed step\n\n| kernel | grid x block | ncu time (us) | share of step |\n|---|---|---:|---:|\n")
+    for k, g, b, t in step:
+        fh.write(f"| {k} | {g} x {b} | {t:.1f} | {100 * t / total:.1f} % |\n")
+    fh.write(f"| **sum** | | **{total:.1f}** | (CUDA-event step in the bench line: {bj['ms_per_step'] * 1e3:.1f} us) |\n\n")
+    fh.write("## `--set full` (per launch)\n\n| kernel | " + " | ".join(l for l, _ in want) + " |\n|---|" + "---:|" * len(want) + "\n")
+    for k, vals in full:
+        fh.write(f"| {k} | " + " | ".join((f"{vals[l]:.1f}" if isinstance(vals[l], float) else str(vals[l])) for l, _ in want) + " |\n")
+    fh.write("\n")
+
+with open(os.path.join(P, "traffic.json"), "w") as fh:
+    json.dump({"source": f"{name} (ncu --set full, per launch)", **traffic}, fh, indent=1)
+print(open(os.path.join(P, f"{name}_summary.md")).read())
