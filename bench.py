@@ -403,7 +403,7 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
                 tj = json.load(fh)
-            traffic = next((v.get("dram_bytes_per_launch") for k, v in tj.items() if k.startswith("logmel_kernel")), None)
+            traffic = next((v.get("dram_bytes_per_launch") for k, v in tj.items() if k.startswith("logmel_kernel") and isinstance(v, dict)), None)
         except Exception:
             pass
         # per-stage algorithmic bytes: valid samples / valid rows only for the ragged stages

@@ -162,6 +162,10 @@ int tasr_conv_lengths_mask(const int32_t* len_in, int32_t batch, int32_t n_layer
                            const int32_t* same_host, int32_t* len_out, float* mask,
                            int32_t mask_width, tasr_stream_t stream);
 
+/* Replaces the audio half of ASRModel.create_masks (model.py:80): mask[i] = any_v (x[i*V + v] != pad_value)
+ * as float32 0/1, i < n.  For audio_inputs [B,T,F,1]: n = B*T*F, V = 1. */
+int tasr_audio_mask(const float* x, int64_t n, int32_t v, float pad_value, float* mask, tasr_stream_t stream);
+
 /* Replaces ASRModel.create_masks + the mask->length reduction (model.py:80, encoder.py:53-56):
  * n_frames[b] = #{t : any_f feat[b,t,f] != 0.0}.  feat [batch, t, f]. */
 int tasr_count_nonzero_frames(const float* feat, int32_t batch, int32_t t, int32_t f,

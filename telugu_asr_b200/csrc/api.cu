@@ -164,13 +164,28 @@ __global__ void conv_lengths_kernel(const int32_t* __restrict__ len_in, int32_t 
   }
 }
 
-__global__ void padding_mask_kernel(const int32_t* __restrict__ len_last, int32_t B, int32_t W,
-                                    float* __restrict__ mask) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t n = (size_t)B * W;
-  if (i >= n) return;
-  int b = (int)(i / W), t = (int)(i % W);
-  mask[i] = (t < len_last[b]) ? 1.0f : 0.0f;
+// Lengths and padding mask in ONE launch: thread (b, t) recomputes the short float32 length chain of its
+// utterance (a handful of instructions) and writes mask[b,t]; the t == 0 thread also stores the lengths.
+__global__ void lengths_mask_kernel(const int32_t* __restrict__ len_in, int32_t B, ConvGeom g, int32_t W,
+                                    int32_t* __restrict__ len_out, float* __restrict__ mask) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * W) return;
+  const int b = (int)(i / W), t = (int)(i - (size_t)b * W);
+  int32_t L = len_in[b];
+  for (int l = 0; l < g.n; ++l) {
+    L = conv_len_f32(L, g.k[l], g.s[l], g.same[l]);
+    if (t == 0) len_out[(size_t)l * B + b] = L;
+  }
+  mask[i] = (t < L) ? 1.0f : 0.0f;
+}
+
+// ASRModel.create_masks' audio half (model.py:80): mask[b,t,f] = any_v (audio[b,t,f,v] != pad) as float32.
+__global__ void audio_mask_kernel(const float* __restrict__ x, size_t n, int32_t V, float pad, float* __restrict__ mask) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int any = 0;
+    for (int v = 0; v < V; ++v) any |= (x[i * V + v] != pad);
+    mask[i] = any ? 1.0f : 0.0f;
+  }
 }
 
 // n_frames[b] = #{t : any_f feat[b,t,f] != 0}  (model.py:80 + encoder.py:53-56).
@@ -213,13 +228,24 @@ extern "C" int tasr_conv_lengths_mask(const int32_t* len_in, int32_t B, int32_t 
   }
   if (B == 0) return TASR_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  conv_lengths_kernel<<<(B + 127) / 128, 128, 0, st>>>(len_in, B, g, len_out);
-  TASR_LAUNCH_CHECK("conv_lengths_kernel");
   if (mask && mask_width > 0) {
-    size_t n = (size_t)B * mask_width;
-    padding_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(len_out + (size_t)(n_layers - 1) * B, B, mask_width, mask);
-    TASR_LAUNCH_CHECK("padding_mask_kernel");
+    const size_t n = (size_t)B * mask_width;
+    lengths_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(len_in, B, g, mask_width, len_out, mask);
+    TASR_LAUNCH_CHECK("lengths_mask_kernel");
+  } else {
+    conv_lengths_kernel<<<(B + 127) / 128, 128, 0, st>>>(len_in, B, g, len_out);
+    TASR_LAUNCH_CHECK("conv_lengths_kernel");
   }
+  return TASR_OK;
+}
+
+extern "C" int tasr_audio_mask(const float* x, int64_t n, int32_t V, float pad_value, float* mask, tasr_stream_t stream) {
+  if (!x || !mask) return fail(TASR_ERR_BAD_ARG, "tasr_audio_mask: null argument");
+  if (n < 0 || V < 1) return fail(TASR_ERR_BAD_ARG, "tasr_audio_mask: bad shape");
+  if (n == 0) return TASR_OK;
+  const long long blocks = (n + 255) / 256;
+  audio_mask_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, V, pad_value, mask);
+  TASR_LAUNCH_CHECK("audio_mask_kernel");
   return TASR_OK;
 }
 

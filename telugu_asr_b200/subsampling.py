@@ -293,4 +293,13 @@ class Conv1DSubsamplingLayer:
     def create_audio_mask(audio_inputs: torch.Tensor, pad_value: float = 0.0) -> torch.Tensor:
         """ASRModel.create_masks' audio half (model.py:80): any(audio != pad, axis=-1) -> [B,T,F] float32.
         Kept for callers that still build the mask the reference's way; passing n_frames is cheaper."""
-        return (audio_inputs != pad_value).any(dim=-1).to(torch.float32)
+        x = _native.require_cuda(audio_inputs, "audio_inputs")
+        if x.dtype != torch.float32:
+            raise ValueError("audio_inputs must be float32")
+        x = x.contiguous()
+        V = x.shape[-1] if x.dim() > 0 else 1
+        out = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _native.check(_native.lib().tasr_audio_mask(x.data_ptr(), out.numel(), int(V), float(pad_value), out.data_ptr(),
+                                                        _native.stream_ptr()))
+        return out

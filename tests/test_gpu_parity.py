@@ -436,3 +436,37 @@ def test_subsampling_ragged_fill_is_bit_identical_to_dense(cuda_device):
     rc = lib.tasr_sepconv1d_tf32_ragged(pl, feats.data_ptr(), nf.data_ptr(), 0, 24, 1498, y.data_ptr(), 745, _native.stream_ptr())
     assert rc == _native.TASR_ERR_BAD_ARG and b"set_pad_row" in lib.tasr_last_error()
     lib.tasr_sepconv_plan_destroy(pl)
+
+
+def test_audio_mask_matches_reference_rule(cuda_device):
+    """ASRModel.create_masks (model.py:80): any(audio != 0.0, axis=-1) on [B,T,F,1] -> [B,T,F] float32."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((3, 50, 80, 1)).astype(np.float32)
+    x[0, 40:] = 0.0
+    x[1, 7, 3] = 0.0
+    x[2, 10] = -0.0            # -0.0 == 0.0 -> masked, like tf.not_equal
+    m = tasr.Conv1DSubsamplingLayer.create_audio_mask(gpu(x, cuda_device)).cpu().numpy()
+    np.testing.assert_array_equal(m, oracle.create_audio_mask_ref(x))
+    assert m.shape == (3, 50, 80) and m.dtype == np.float32
+
+
+def test_shard_union_equals_single_gpu_bitwise(cuda_device):
+    """utterances shard by length over ranks with no data-path collective, so the
+    union of the per-shard results must be the single-batch result bit for bit (here: both shards on
+    this GPU, each padded to its own local maximum, as the ranks do)."""
+    from telugu_asr_b200.synth import draw_lengths
+    lens = draw_lengths(32, 8000, 120000, seed=11)
+    wav, ln = oracle.make_waveforms(lens, seed=11, dist="tilt")
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    fe = tasr.FrontEnd(math="tf32")
+    fe.set_weights(weights, cuda_device)
+    out, mask, len3 = _call_or_skip(fe, gpu(wav, cuda_device), gpu(ln, cuda_device), max_length=int(ln.max()))
+    for world in (2, 4):
+        for shard in tasr.shard_by_length(ln, world):
+            nm = -(-int(ln[shard].max()) // 4) * 4
+            o, m, l3 = fe(gpu(wav[shard][:, :nm], cuda_device), gpu(ln[shard], cuda_device), max_length=int(ln[shard].max()))
+            assert torch.equal(l3, len3[shard])
+            for j, i in enumerate(shard):
+                L = int(l3[j])
+                assert torch.equal(o[j, :L], out[i, :L])                    # valid encoder input, bit for bit
+                assert torch.equal(m[j, :L], mask[i, :L]) and not m[j, L:].any()
