@@ -162,6 +162,16 @@ int tasr_conv_lengths_mask(const int32_t* len_in, int32_t batch, int32_t n_layer
                            const int32_t* same_host, int32_t* len_out, float* mask,
                            int32_t mask_width, tasr_stream_t stream);
 
+/* SpecAugment, deterministic half (replaces FreqMasking.augment / TimeMasking.augment,
+ * src/augmentations/specaugment.py:6-62, applied per utterance at src/dataset.py:172): in place on
+ * feat [batch, t_max, f]: feat[b,t,:] *= 0 for t in [t0, t0+t) of every time mask, feat[b,:,k] *= 0 for
+ * k in [f0, f0+f) of every frequency mask, rows t < n_frames[b] only.  time_masks [batch, n_time, 2] =
+ * (t0, t), freq_masks [batch, n_freq, 2] = (f0, f), device int32; a mask of width 0 is "not applied"
+ * (the reference applies each augmentation with probability `prob`).  The draws are the caller's. */
+int tasr_specaugment_f32(float* feat, const int32_t* n_frames, int32_t batch, int32_t t_max, int32_t f,
+                         const int32_t* time_masks, int32_t n_time, const int32_t* freq_masks, int32_t n_freq,
+                         tasr_stream_t stream);
+
 /* Replaces the audio half of ASRModel.create_masks (model.py:80): mask[i] = any_v (x[i*V + v] != pad_value)
  * as float32 0/1, i < n.  For audio_inputs [B,T,F,1]: n = B*T*F, V = 1. */
 int tasr_audio_mask(const float* x, int64_t n, int32_t v, float pad_value, float* mask, tasr_stream_t stream);

@@ -37,3 +37,4 @@ from .subsampling_ref import (  # noqa: F401
     glorot_subsampling_weights,
 )
 from .synth import make_waveforms  # noqa: F401
+from . import specaugment_ref  # noqa: F401

@@ -10,6 +10,7 @@ from .subsampling import Conv1DSubsamplingLayer, get_conv_length  # noqa: F401
 from .frontend import FrontEnd, REFERENCE_SPEECH_CONFIG, REFERENCE_SUBSAMPLING_CONFIG, load_reference_yaml  # noqa: F401
 from .collate import pack_waveforms, PinnedBatch, PackedBatch, shard_by_length  # noqa: F401
 
+from .augmentation import Augmentation, FreqMasking, TimeMasking, AUGMENTATIONS  # noqa: F401
 from .pipeline import FrontEndPipeline, Ticket  # noqa: F401
 
 __version__ = "0.1.0"

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "tasr_sepconv1d_tf32_ragged": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp]),
     "tasr_conv_lengths_mask": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32),
                                          C.POINTER(_i32), _vp, _vp, _i32, _vp]),
+    "tasr_specaugment_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp]),
     "tasr_audio_mask": (C.c_int, [_vp, _i64, _i32, C.c_float, _vp, _vp]),
     "tasr_count_nonzero_frames": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
 }
