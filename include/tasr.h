@@ -51,10 +51,16 @@ typedef struct TasrFeatParams {
   int32_t num_mel_bins;     /* num_feature_bins = 80                                         */
   int32_t normalize_signal; /* 1: x *= 1/(max|x|+1e-9) per utterance (:68-72)                */
   int32_t log_base_e;       /* 0: log10 (log_base "10"), 1: natural log (:107-110)           */
-  int32_t pad_end;          /* must be 0 (config/model.yaml:8); 1 is TASR_ERR_UNSUPPORTED     */
+  int32_t pad_end;          /* 0 (config/model.yaml:8); 1: tf.signal.stft(pad_end=True), ceil(N/step) frames */
   float preemphasis;        /* 0.97; <= 0 disables (:74-79)                                  */
   float output_floor;       /* 1e-9 (:109)                                                   */
+  int32_t feature_type;     /* TASR_FEAT_* (:136-153); 0 = log_mel_spectrogram               */
+  int32_t normalize_zscore; /* 1: per frame (x-mean)/sqrt(var+1e-9) over the feature axis (:82-85)   */
+  int32_t normalize_min_max;/* 1: per frame (x-min)/(max-min) (:86-91); zscore wins if both are set  */
 } TasrFeatParams;
+
+/* feature_type codes (FeaturizerConfig, src/speech_featurizer.py:10-15). */
+enum { TASR_FEAT_LOG_MEL = 0, TASR_FEAT_SPECTROGRAM = 1, TASR_FEAT_MFCC = 2, TASR_FEAT_WAVEFORM = 3 };
 
 /* One SeparableConv1D layer (encoder.py:31-40), weights on the DEVICE, float32:
  * dw [kernel, c_in] (Keras depthwise_kernel (k,Cin,1)), pw [c_in, c_out] (pointwise_kernel
@@ -109,8 +115,16 @@ int tasr_unpack_pcm16(const int16_t* packed, const int64_t* offset, const int32_
 int tasr_absmax_f32(const float* wav, const int32_t* len, int32_t batch, int64_t row_stride,
                     float* peak, tasr_stream_t stream);
 
+/* Replaces SpeechFeaturizer.call with feature_type "waveform" (src/speech_featurizer.py:132-133,142-143):
+ * out[b, n] = preemphasis(normalize_signal(wav[b, :len[b]]))[n] for n < len[b]; samples beyond len[b] of
+ * out are not written.  out has the layout of wav (same row stride). */
+int tasr_waveform_f32(const TasrFeaturizer* f, const float* wav, const int32_t* len, const float* peak_or_null,
+                      int32_t batch, int64_t row_stride, float* out, tasr_stream_t stream);
+
 /* Replaces SpeechFeaturizer.call on each utterance (src/speech_featurizer.py:136-161:
- * normalize_signal -> preemphasis_signal -> stft -> mel matmul -> logarithm) AND the
+ * normalize_signal -> preemphasis_signal -> stft -> mel matmul -> logarithm; for the other feature types
+ * of the handle: spectrogram = log power of the first num_mel_bins FFT bins (:124-126), mfcc = DCT-II of
+ * the log-mel (:128-130); then normalize_audio_feature (:81-93) when the handle asks for it) AND the
  * zero-padded collate that follows it (src/dataset.py:173-175, 236-252).
  * wav [batch, row_stride] (samples beyond len[b] are never read); peak from
  * tasr_absmax_f32 (may be NULL when params.normalize_signal == 0);

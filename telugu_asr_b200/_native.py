@@ -21,8 +21,12 @@ class TasrFeatParams(C.Structure):
         ("sample_rate", C.c_int32), ("frame_length", C.c_int32), ("frame_step", C.c_int32),
         ("fft_length", C.c_int32), ("num_mel_bins", C.c_int32), ("normalize_signal", C.c_int32),
         ("log_base_e", C.c_int32), ("pad_end", C.c_int32), ("preemphasis", C.c_float),
-        ("output_floor", C.c_float),
+        ("output_floor", C.c_float), ("feature_type", C.c_int32), ("normalize_zscore", C.c_int32),
+        ("normalize_min_max", C.c_int32),
     ]
+
+
+FEATURE_TYPES = {"log_mel_spectrogram": 0, "spectrogram": 1, "mfcc": 2, "waveform": 3}
 
 
 class TasrSepConvLayer(C.Structure):
@@ -43,6 +47,7 @@ _SIGNATURES = {
     "tasr_featurizer_uses_fixed_mel": (C.c_int, [_vp]),
     "tasr_unpack_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     "tasr_unpack_pcm16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "tasr_waveform_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "tasr_absmax_f32": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "tasr_logmel_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _vp, _vp]),
     "tasr_sepconv1d_f32": (C.c_int, [_vp, _i32, _i32, C.POINTER(TasrSepConvLayer), _vp, _i32, _vp]),

@@ -54,7 +54,8 @@ extern "C" int tasr_featurizer_create(const TasrFeatParams* p, const float* hann
                 "tasr_featurizer_create: kernels are specialised for frame_length=400, frame_step=160, "
                 "fft_length=512, num_mel_bins=80 (config/model.yaml); got %d/%d/%d/%d",
                 p->frame_length, p->frame_step, p->fft_length, p->num_mel_bins);
-  if (p->pad_end) return fail(TASR_ERR_UNSUPPORTED, "tasr_featurizer_create: pad_end=True is not built");
+  if (p->feature_type < TASR_FEAT_LOG_MEL || p->feature_type > TASR_FEAT_WAVEFORM)
+    return fail(TASR_ERR_BAD_ARG, "tasr_featurizer_create: unknown feature_type %d", p->feature_type);
   if (!(p->output_floor > 0.0f)) return fail(TASR_ERR_BAD_ARG, "tasr_featurizer_create: output_floor must be > 0");
   if (p->output_floor < 1.17549435e-38f)
     return fail(TASR_ERR_UNSUPPORTED, "tasr_featurizer_create: output_floor below FLT_MIN (the log uses a flush-to-zero MUFU)");
@@ -116,6 +117,15 @@ extern "C" int tasr_featurizer_create(const TasrFeatParams* p, const float* hann
   if (rc == TASR_OK) rc = check_cuda(cudaMemcpy(f->d_tw512, tw512.data(), 256 * sizeof(float2), cudaMemcpyHostToDevice), "copy tw512");
   if (rc == TASR_OK) rc = check_cuda(cudaMemcpy(f->d_band_w, bw.data(), kMelBandMaxW4 * sizeof(float4), cudaMemcpyHostToDevice), "copy band_w");
   if (rc == TASR_OK) rc = check_cuda(cudaMemcpy(f->d_bands, &bands, sizeof(MelBands), cudaMemcpyHostToDevice), "copy bands");
+  if (rc == TASR_OK && p->feature_type == TASR_FEAT_MFCC) {
+    // tf.signal.mfccs_from_log_mel_spectrograms: dct(type 2, unnormalised: 2 sum x_n cos(pi k (2n+1)/(2M))) * rsqrt(2M)
+    std::vector<float> dct((size_t)kMel * kMel);
+    const double pi = 3.14159265358979323846, sc = 2.0 / sqrt(2.0 * kMel);
+    for (int n = 0; n < kMel; ++n)
+      for (int k = 0; k < kMel; ++k) dct[(size_t)n * kMel + k] = (float)(sc * cos(pi * k * (2.0 * n + 1.0) / (2.0 * kMel)));
+    rc = check_cuda(cudaMalloc(&f->d_dct, dct.size() * sizeof(float)), "cudaMalloc dct");
+    if (rc == TASR_OK) rc = check_cuda(cudaMemcpy(f->d_dct, dct.data(), dct.size() * sizeof(float), cudaMemcpyHostToDevice), "copy dct");
+  }
   if (rc != TASR_OK) { tasr_featurizer_destroy(f); return rc; }
   *out = f;
   return TASR_OK;
@@ -128,6 +138,7 @@ extern "C" int tasr_featurizer_destroy(TasrFeaturizer* f) {
   cudaFree(f->d_tw512);
   cudaFree(f->d_band_w);
   cudaFree(f->d_bands);
+  cudaFree(f->d_dct);
   delete f;
   return TASR_OK;
 }

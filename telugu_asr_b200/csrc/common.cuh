@@ -78,9 +78,14 @@ struct TasrFeaturizer {
   tasr::MelBands* d_bands;  // device copy of `bands`
   tasr::MelBands bands; // host copy
   float log_scale;      // log10(2) or ln(2)
+  float* d_dct;         // [80][80] mfcc basis D[n][k] = 2 cos(pi k (2n+1) / 160) / sqrt(160), or null
   int mel_fixed;        // 1: the matrix has the compiled-in config/model.yaml structure (mel_geometry.inc)
   float mel_fixed_w[512];  // wr[256] | wf[256], per FFT bin (kernel-parameter constants of the unrolled projection)
 };
+
+// feature_post.cu: mfcc DCT and/or per-frame z-score / min-max normalisation, in place on [B, T_max, 80].
+int tasr_feature_post_launch(const TasrFeaturizer* f, float* feat, const int32_t* n_frames, int32_t B, int32_t T_max,
+                             cudaStream_t st);
 
 // logmel.cu: true (and wr_wf_512 filled) when the dense [257,80] matrix has the compiled-in structure.
 bool tasr_mel_fixed_from_dense(const float* mel_w_host, float* wr_wf_512);

@@ -136,12 +136,15 @@ struct LogmelArgs {
   int64_t row_stride;
   int32_t B, T_max, tiles_per_row;
   int32_t normalize;
+  int32_t pad_end;         // tf.signal.stft(pad_end=True): ceil(N/160) frames, the tail zero padded
+  int32_t mode;            // 0: mel projection + log; 1: log of the first 80 power bins ("spectrogram")
   float preemph, floor_, log_scale;
 };
 
-__device__ __forceinline__ int frames_of(int n, int T_max) {
-  const int Tb = (n >= kFrameLen) ? 1 + (n - kFrameLen) / kFrameStep : 0;
-  return min(Tb, T_max);
+__device__ __forceinline__ int frames_of(int n, const LogmelArgs& a) {   // src/speech_featurizer.py:163-166
+  const int Tb = a.pad_end ? (n > 0 ? (n + kFrameStep - 1) / kFrameStep : 0)
+                           : ((n >= kFrameLen) ? 1 + (n - kFrameLen) / kFrameStep : 0);
+  return min(Tb, a.T_max);
 }
 
 // ---- fixed-geometry mel projection (config/model.yaml filterbank), fully unrolled ------------------
@@ -179,7 +182,7 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
   const int t = lane & 15, half = lane >> 4;
 
   // ---- n_frames (src/speech_featurizer.py:163-166) -------------------------------------------
-  for (int b = blockIdx.x * kThreads + tid; b < a.B; b += gridDim.x * kThreads) a.n_frames[b] = frames_of(a.len[b], a.T_max);
+  for (int b = blockIdx.x * kThreads + tid; b < a.B; b += gridDim.x * kThreads) a.n_frames[b] = frames_of(a.len[b], a);
 
   // ---- per-lane constants ----------------------------------------------------------------
   float2 hw[13];
@@ -219,7 +222,7 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
       const int u = 4 * tid + i;
       vt[i] = pt[i] = 0;
       if (u < nu) {
-        vt[i] = (frames_of(a.len[cb + u], a.T_max) + kTileFrames - 1) / kTileFrames;
+        vt[i] = (frames_of(a.len[cb + u], a) + kTileFrames - 1) / kTileFrames;
         const int pad_rows = a.T_max - vt[i] * kTileFrames;
         pt[i] = pad_rows > 0 ? (pad_rows + kPadChunkRows - 1) / kPadChunkRows : 0;
       }
@@ -291,7 +294,7 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
     }
 
     const int n = a.len[b];
-    const int Tb = frames_of(n, a.T_max);
+    const int Tb = frames_of(n, a);
     const int f0 = tf * kTileFrames;
     const int rows = min(kTileFrames, a.T_max - f0);
     const int nvalid = min(kTileFrames, Tb - f0);   // >= 1: only valid tiles are enumerated
@@ -301,7 +304,8 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
     {
       const float* row = a.wav + (size_t)b * a.row_stride;
       const int s0 = f0 * kFrameStep;
-      const int count = (nvalid - 1) * kFrameStep + kFrameLen;  // multiple of 4, s0+count <= n
+      const int count = (nvalid - 1) * kFrameStep + kFrameLen;  // multiple of 4; s0+count <= n unless pad_end
+      const int lim = a.pad_end ? min(count, n - s0) : count;   // samples of the tile that exist
       float g = 1.0f;
       if (a.normalize) g = __fdiv_rn(1.0f, __fadd_rn(a.peak[b], 1e-9f));  // :70
       const float c = a.preemph;
@@ -313,8 +317,8 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
         const int s = s0 + 4 * i4;
         x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         xp[u] = 0.0f;
-        if (4 * i4 < count) {
-          x[u] = *reinterpret_cast<const float4*>(row + s);
+        if (4 * i4 < lim) {
+          x[u] = *reinterpret_cast<const float4*>(row + s);   // (rows are padded to 4 samples: in bounds)
           if (s > 0) xp[u] = row[s - 1];
         }
       }
@@ -331,6 +335,12 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
             y.y = __fsub_rn(v.y, __fmul_rn(c, v.x));
             y.z = __fsub_rn(v.z, __fmul_rn(c, v.y));
             y.w = __fsub_rn(v.w, __fmul_rn(c, v.z));
+          }
+          if (a.pad_end) {   // the zero padding is appended AFTER pre-emphasis (tf.signal.frame pads the signal it is given)
+            if (4 * i4 + 0 >= lim) y.x = 0.0f;
+            if (4 * i4 + 1 >= lim) y.y = 0.0f;
+            if (4 * i4 + 2 >= lim) y.z = 0.0f;
+            if (4 * i4 + 3 >= lim) y.w = 0.0f;
           }
           *reinterpret_cast<float4*>(S.wav + 4 * i4) = y;
         }
@@ -406,7 +416,9 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
     {
       const float* Prow = S.P + lane * kPStride;
       float* srow = stage + lane * kOutStride;
-      if (FIXED) {
+      if (a.mode == 1) {   // "spectrogram": log power of the first 80 FFT bins (src/speech_featurizer.py:124-126)
+        for (int k = warp; k < kMel; k += kWarps) srow[k] = lg2_normal(fmaxf(Prow[k], a.floor_)) * a.log_scale;
+      } else if (FIXED) {
         switch (warp) {
           case 0: mel_fixed_group<0>(Prow, mw, srow, a.floor_, a.log_scale); break;
           case 1: mel_fixed_group<1>(Prow, mw, srow, a.floor_, a.log_scale); break;
@@ -467,6 +479,8 @@ extern "C" int tasr_logmel_f32(const TasrFeaturizer* f, const float* wav, const 
     return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32: normalize_signal is set but peak is NULL (run tasr_absmax_f32 first)");
   if (!aligned16(wav) || (row_stride & 3) || !aligned16(out))
     return fail(TASR_ERR_MISALIGNED, "tasr_logmel_f32: wav/out must be 16-byte aligned and row_stride a multiple of 4 samples");
+  if (f->p.feature_type == TASR_FEAT_WAVEFORM)
+    return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32: the handle's feature_type is 'waveform'; call tasr_waveform_f32");
   if (B == 0) return TASR_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0;
@@ -488,6 +502,8 @@ extern "C" int tasr_logmel_f32(const TasrFeaturizer* f, const float* wav, const 
   a.hwin = f->d_hwin; a.tw256 = f->d_tw256; a.tw512 = f->d_tw512; a.band_w = f->d_band_w; a.bands = f->d_bands;
   a.row_stride = row_stride; a.B = B; a.T_max = T_max; a.tiles_per_row = tiles_per_row;
   a.normalize = f->p.normalize_signal ? 1 : 0;
+  a.pad_end = f->p.pad_end ? 1 : 0;
+  a.mode = (f->p.feature_type == TASR_FEAT_SPECTROGRAM) ? 1 : 0;
   a.preemph = f->p.preemphasis; a.floor_ = f->p.output_floor; a.log_scale = f->log_scale;
   // Persistent grid: two CTAs per SM; never more CTAs than work items (valid tiles + padding chunks <= total + B).
   const long long cap = total + B;
@@ -500,6 +516,8 @@ extern "C" int tasr_logmel_f32(const TasrFeaturizer* f, const float* wav, const 
     logmel_kernel<false><<<grid, kThreads, smem, st>>>(a, zero_w);
   }
   TASR_LAUNCH_CHECK("logmel_kernel");
+  if (f->p.feature_type == TASR_FEAT_MFCC || f->p.normalize_zscore || f->p.normalize_min_max)
+    return tasr_feature_post_launch(f, out, n_frames, B, T_max, st);
   return TASR_OK;
 }
 

@@ -98,14 +98,13 @@ class SpeechFeaturizer:
         return self._hann, self._mel_w
 
     def _check_supported(self):
-        if self.feature_type != "log_mel_spectrogram":
-            raise NotImplementedError(
-                f"feature_type={self.feature_type!r}: only 'log_mel_spectrogram' (config/model.yaml:6) has a "
-                "B200 kernel in this revision")
-        if self._normalize_zscore or self._normalize_min_max:
-            raise NotImplementedError("normalize_zscore / normalize_min_max (False in config/model.yaml:15-16) are not built")
         if self.padding and self.padding > 0:
             raise NotImplementedError("padding > 0 (0.0 in config/model.yaml:17; the reference branch fails on 1-D input)")
+        if self.feature_type != "waveform" and (self.frame_length, self.frame_step, self.num_feature_bins) != (400, 160, 80):
+            raise NotImplementedError(
+                "the B200 kernels are specialised for 25 ms / 10 ms frames at 16 kHz and 80 feature bins "
+                f"(config/model.yaml:1-5); got frame_length={self.frame_length}, frame_step={self.frame_step}, "
+                f"num_feature_bins={self.num_feature_bins}")
 
     def _handle(self, device: torch.device) -> int:
         idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -120,7 +119,8 @@ class SpeechFeaturizer:
             normalize_signal=int(bool(self._normalize_signal)), log_base_e=int(self.log_base == "e"),
             pad_end=int(bool(self.pad_end)),
             preemphasis=float(self.preemphasis) if self.preemphasis else 0.0,
-            output_floor=float(self.output_floor))
+            output_floor=float(self.output_floor), feature_type=_native.FEATURE_TYPES[self.feature_type],
+            normalize_zscore=int(bool(self._normalize_zscore)), normalize_min_max=int(bool(self._normalize_min_max)))
         out = C.c_void_p()
         with torch.cuda.device(idx):
             _native.check(_native.lib().tasr_featurizer_create(
@@ -171,6 +171,8 @@ class SpeechFeaturizer:
         x = _native.require_cuda(inputs, "inputs")
         if x.dtype != torch.float32:
             raise ValueError(f"inputs must be float32 (the reference decodes audio to float32); got {x.dtype}")
+        if self.feature_type == FeaturizerConfig.waveform:
+            return self._waveform(x, lengths)
         if x.dim() == 1:
             if lengths is not None:
                 raise ValueError("lengths is only meaningful for batched [B, N_max] inputs")
@@ -181,6 +183,35 @@ class SpeechFeaturizer:
         return self.featurize_batch(x, lengths, out=out)
 
     call = __call__
+
+    def _waveform(self, x: torch.Tensor, lengths):
+        """feature_type 'waveform' (src/speech_featurizer.py:132-133): the normalised, pre-emphasised signal.
+        [N] -> [N]; [B, N_max] (+ lengths) -> [B, N_max] with zeros beyond each length."""
+        one = x.dim() == 1
+        wav = (x.unsqueeze(0) if one else x).contiguous()
+        if wav.dim() != 2:
+            raise ValueError(f"inputs must be [N] or [B, N_max]; got shape {tuple(x.shape)}")
+        B, n_max = wav.shape
+        n_pad = -(-max(n_max, 1) // 4) * 4
+        buf = torch.zeros((B, n_pad), dtype=torch.float32, device=wav.device)
+        buf[:, :n_max] = wav
+        if lengths is None:
+            lengths = torch.full((B,), n_max, dtype=torch.int32, device=wav.device)
+        lengths = _native.require_cuda(lengths, "lengths").to(torch.int32).contiguous()
+        out = torch.zeros_like(buf)
+        if B and n_max:
+            h = self._handle(wav.device)
+            L = _native.lib()
+            with torch.cuda.device(wav.device):
+                st = _native.stream_ptr()
+                peak_ptr = None
+                if self._normalize_signal:
+                    peak = torch.empty((B,), dtype=torch.float32, device=wav.device)
+                    _native.check(L.tasr_absmax_f32(buf.data_ptr(), lengths.data_ptr(), B, n_pad, peak.data_ptr(), st))
+                    peak_ptr = peak.data_ptr()
+                _native.check(L.tasr_waveform_f32(h, buf.data_ptr(), lengths.data_ptr(), peak_ptr, B, n_pad, out.data_ptr(), st))
+        out = out[:, :n_max]
+        return out[0] if one else out
 
     # ------------------------------------------------------------------ batched device path
     def featurize_batch(self, wav: torch.Tensor, lengths: torch.Tensor | None, out: torch.Tensor | None = None,

@@ -470,3 +470,56 @@ def test_shard_union_equals_single_gpu_bitwise(cuda_device):
                 L = int(l3[j])
                 assert torch.equal(o[j, :L], out[i, :L])                    # valid encoder input, bit for bit
                 assert torch.equal(m[j, :L], mask[i, :L]) and not m[j, L:].any()
+
+
+@pytest.mark.parametrize("name,over", [
+    ("spectrogram", dict(feature_type="spectrogram")),
+    ("mfcc", dict(feature_type="mfcc")),
+    ("zscore", dict(normalize_zscore=True)),
+    ("minmax", dict(normalize_min_max=True)),
+    ("spectrogram_minmax", dict(feature_type="spectrogram", normalize_min_max=True)),
+    ("mfcc_zscore_ln", dict(feature_type="mfcc", normalize_zscore=True, log_base="e")),
+    ("pad_end", dict(pad_end=True)),
+    ("pad_end_nopre", dict(pad_end=True, preemphasis=0.0, normalize_signal=False)),
+])
+def test_featurizer_other_modes(cuda_device, name, over):
+    """the feature types and normalisations that config/model.yaml leaves off
+    (src/speech_featurizer.py:81-93,124-133, pad_end :163-166), against the oracle with the same parameters.
+    Tolerance: max(1e-4, 4 x the float32 oracle's own distance from the float64 oracle)."""
+    cfg = dict(tasr.REFERENCE_SPEECH_CONFIG, **over)
+    f = tasr.SpeechFeaturizer(**cfg)
+    p = oracle.FeatParams(**cfg)
+    lens = [16000, 5281, 400, 399, 24001, 161, 1, 0]
+    wav, ln = oracle.make_waveforms(lens, seed=47, dist="tilt")
+    for b, L in enumerate(lens):
+        wav[b, L:] = np.nan                     # never read, pad_end included
+    out, nf = run_logmel(f, wav, ln, cuda_device)
+    clean = np.nan_to_num(wav, nan=0.0)
+    ref64, nref = oracle.logmel_batch_ref(clean, ln, p, dtype=np.float64)
+    ref32, _ = oracle.logmel_batch_ref(clean, ln, p, dtype=np.float32)
+    np.testing.assert_array_equal(nf, nref)                                    # bit-exact frame counts
+    assert [f.get_nframes(int(L)) if L >= (1 if p.pad_end else 400) else 0 for L in lens] == nref.tolist()
+    assert out.shape == ref64.shape and np.isfinite(out).all()
+    tol = max(LOGMEL_TOL, 4.0 * float(np.abs(ref32 - ref64).max()))
+    assert np.abs(out - ref64).max() <= tol, (name, np.abs(out - ref64).max(), tol)
+    for b, t in enumerate(nf):
+        assert not out[b, t:].any()
+    one = f(gpu(clean[0, : lens[0]].copy(), cuda_device)).cpu().numpy()         # 1-D call, same values
+    np.testing.assert_array_equal(one, out[0, : nf[0], :, 0])
+
+
+def test_featurizer_waveform_mode(cuda_device):
+    """feature_type 'waveform' (src/speech_featurizer.py:132-133): normalize_signal + preemphasis only, bit for bit
+    (each op is one float32 rounding in the reference's order)."""
+    f = tasr.SpeechFeaturizer(**dict(tasr.REFERENCE_SPEECH_CONFIG, feature_type="waveform"))
+    p = oracle.FeatParams(**dict(tasr.REFERENCE_SPEECH_CONFIG, feature_type="waveform"))
+    assert f.compute_output_shape((2, 16000)) == (2, None, 1)
+    lens = [16000, 5, 1, 0, 4097]
+    wav, ln = oracle.make_waveforms(lens, seed=49, dist="tilt")
+    out = f(gpu(wav, cuda_device), gpu(ln, cuda_device)).cpu().numpy()
+    for b, L in enumerate(lens):
+        ref = oracle.featurizer_ref.featurize_ref(wav[b, :L], p, dtype=np.float32)
+        np.testing.assert_array_equal(out[b, :L], ref)
+        assert not out[b, L:].any()
+    one = f(gpu(wav[0, :16000].copy(), cuda_device)).cpu().numpy()
+    np.testing.assert_array_equal(one, out[0, :16000])
