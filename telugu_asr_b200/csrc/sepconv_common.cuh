@@ -1,0 +1,171 @@
+// Shared pieces of the TF32 separable-convolution kernels (sepconv_tf32.cu: one CTA per tile;
+// sepconv_ws.cu: persistent, warp-specialised): the plan, PTX wrappers for mbarrier / TMA bulk copy /
+// tcgen05, UMMA descriptors, the SFU activations and the argument block.
+#pragma once
+#include "common.cuh"
+
+struct TasrSepConvPlan {
+  TasrSepConvLayer L;   // dw / bias pointers are borrowed from the caller (must outlive the plan)
+  int device;
+  int n_split;          // output channels are processed in n_split slices of NT
+  int NT;
+  int n_chunks;         // ceil(c_in / 32)
+  float* d_bpack;       // [n_split][n_chunks][NT*32] shared-memory images of pw^T
+  void* kernel;         // template instance for (c_in, activation)
+  float* d_pad_in;      // [9][c_in]  nine copies of the input's padding row (ragged mode)
+  float* d_pad_out;     // [c_out]    this layer's output for an all-padding receptive field
+  int pad_ready;
+  int use_ws;           // 1: persistent warp-specialised kernel (sepconv_ws.cu) when the shape allows it
+};
+
+namespace tasr_sep {
+
+constexpr int kThreads = 256;
+constexpr int kMT = 128;                 // output frames per tile (UMMA M)
+constexpr int kKC = 32;                  // input channels per chunk (one 128-byte swizzle row)
+constexpr int kRun = kMT / (kThreads / 32);   // 16 output frames per warp
+constexpr int kWin = 2 * (kRun - 1) + 9; // 39 input rows per run
+constexpr int kABytes = kMT * kKC * 4;   // 16 KiB per stage
+constexpr int kTmemCols = 256;
+constexpr int kStgStride = 36;           // floats; conflict-free for 128-bit row writes and reads
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, TF32 inputs, FP32 accumulate.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 B
+// apart (stride byte offset), descriptor version 1 (sm_100).  `saddr` must be 1024-byte aligned
+// (+ 32*k bytes to step along K inside the swizzle row).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                 // leading byte offset: unused for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
+  d |= (uint64_t)1 << 46;                 // version
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor: D=F32, A=B=TF32, both K-major, N, M.
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// tanh(z) = 1 - 2/(1 + e^{2z}) on the SFU (ex2 + rcp): absolute error < 3e-7 over the whole range,
+// saturates correctly (e -> inf gives 1, e -> 0 gives -1).
+__device__ __forceinline__ float tanh_fast(float z) {
+  const float e = ex2_approx(z * 2.88539008177792681472f);   // 2*log2(e)
+  return fmaf(-2.0f, rcp_approx(1.0f + e), 1.0f);
+}
+// Exact-erf GELU (Keras approximate=False): 0.5 z (1 + erf(z/sqrt2)), with erf from Abramowitz &
+// Stegun 7.1.26 (|error| <= 1.5e-7): erfc(u) = t(a1 + t(a2 + t(a3 + t(a4 + t a5)))) e^{-u^2},
+// t = 1/(1 + p u), u = |z|/sqrt2.  gelu = z - (z/2) s for z >= 0 and (z/2) s for z < 0, s = erfc(u).
+__device__ __forceinline__ float gelu_erf_fast(float z) {
+  const float u = fabsf(z) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float s = p * t * ex2_approx(u * u * -1.44269504088896340736f);
+  const float hz = 0.5f * z;
+  return (z >= 0.0f) ? fmaf(-hz, s, z) : hz * s;
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_apply(float z) {
+  if (ACT == TASR_ACT_TANH) return tanh_fast(z);
+  if (ACT == TASR_ACT_GELU_ERF) return gelu_erf_fast(z);
+  if (ACT == TASR_ACT_RELU) return fmaxf(z, 0.0f);
+  return z;
+}
+
+struct SepArgs {
+  const float* x;
+  const float* dw;
+  const float* bpack;
+  const float* bias;
+  float* y;
+  int32_t T_in, T_out, C_in, C_out, NT, n_chunks, act;
+  // ragged mode (len0 != nullptr): rows t >= ceil(len0[b] / 2^shift) of x[b] all equal the padding row the
+  // plan was given, so a tile whose receptive field starts there is the constant row pad_out: filled, not computed.
+  const int32_t* len0;
+  const float* pad_out;
+  int32_t shift;
+};
+
+}  // namespace tasr_sep
+
+// sepconv_ws.cu: launches the persistent warp-specialised kernel; returns a negative value (and launches
+// nothing) when the shape is outside its limits, so that the caller falls back to the per-tile kernel.
+int tasr_sepconv_ws_launch(const TasrSepConvPlan* p, const tasr_sep::SepArgs& sa, int32_t B, cudaStream_t st);

@@ -1,0 +1,438 @@
+// SeparableConv1D forward, persistent warp-specialised TF32 kernel (sm_100a).  EXPERIMENTAL, opt-in
+// (TASR_SEPCONV_WS=1 at plan creation); the default is the per-tile kernel of sepconv_tf32.cu.
+//
+// Same arithmetic, operand layouts and summation order as sepconv_tf32.cu (its output is bit-identical,
+// tested); what changes is the schedule.  sepconv_tf32_kernel runs one CTA per 128-frame tile and walks
+// its channel chunks in lock step (depthwise -> barrier -> MMA issue).  Here ONE CTA per SM lives for the
+// whole layer and its warps take roles:
+//
+//   warps 0-15  depthwise producers: lane <-> channel, a run of 8 output frames per warp, 23-row register
+//               sliding window straight from global memory (the next tile's window is pulled into L2 by
+//               cp.async.bulk.prefetch a tile ahead), result rounded to TF32 into a 3-deep A ring (UMMA
+//               K-major SWIZZLE_128B), mbarrier hand-off per stage — no CTA-wide barrier;
+//   warps 16-23 epilogue: tcgen05.ld -> +bias -> activation (SFU) -> per-warp transpose in shared memory ->
+//               128-bit coalesced stores, overlapped with the next tile's main loop; they also write the
+//               constant padding rows of the ragged mode (tiles that lie entirely in the collate padding);
+//   warp 24     B loader: cp.async.bulk (TMA bulk copy) of the packed pw^T chunk into a 4-deep B ring;
+//   warp 25     MMA issuer: tcgen05.mma kind::tf32, M=128, N=NT, accumulators double-buffered in TMEM
+//               (2 x NT columns of the 512), tcgen05.commit frees ring stages and publishes accumulators.
+//
+// Work distribution: the tiles that need computing are enumerated through a block-wide prefix sum over the
+// utterances (ragged: ceil(cf/256) tiles per utterance, cf = ceil(n_frames / 2^layer)) and dealt round-robin
+// to the CTAs, so every SM gets the same number +-1; the padding tiles are dealt the same way.
+//
+// Status (round 1, B200, config 3): 66 / 89 / 75 us for the three layers against 67 / 98 / 72 us for the
+// per-tile kernel — no better.  A globaltimer trace of CTA 0 (tools/ws_trace.py) and ablations show a
+// cadence of ~0.9-1.2 us per 32-channel chunk that survives removing the depthwise loads, the depthwise
+// arithmetic, the B copies and the epilogue alike (the bare role/mbarrier/MMA skeleton alone takes
+// 29 / 41 / 37 us), i.e. the hand-offs between the roles, not bandwidth or arithmetic, pace the kernel.
+// Kept because it is bit-exact and is the starting point for round 2 (fewer, fatter hand-offs: K=64 or
+// K=96 per stage, one elected poller per warp, TMA-staged input tiles).
+#include "sepconv_common.cuh"
+
+using namespace tasr;
+using namespace tasr_sep;
+
+namespace {
+
+constexpr int kDwWarps = 16;
+constexpr int kRunWs = kMT / kDwWarps;          // 8 output frames per depthwise warp
+constexpr int kWinWs = 2 * (kRunWs - 1) + 9;    // 23 input rows per run
+constexpr int kEpWarps = 8;
+constexpr int kWsThreads = (kDwWarps + kEpWarps + 2) * 32;   // 576
+constexpr int kStagesA = 3;   // depthwise -> MMA ring (16 KB each)
+constexpr int kStagesB = 4;   // pw^T chunk ring (NT*128 B each): deep enough to cover the L2 -> shared latency of the bulk copies
+constexpr int kMaxUtt = 1024;     // utterances indexed in shared memory
+constexpr int kListCap = 256;    // work items per CTA
+constexpr int kTmemColsWs = 512;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+struct WsLayout {
+  uint32_t a, b, stg, bias, cum_c, cum_f, list_c, list_cf, list_f, bars, tmem_slot, total;
+};
+__host__ __device__ inline WsLayout ws_layout(int NT, int C_out) {
+  WsLayout L;
+  uint32_t o = 0;
+  L.a = o; o += kStagesA * kABytes;
+  L.b = o; o += kStagesB * (uint32_t)NT * 128u;
+  L.stg = o; o += kEpWarps * 32 * kStgStride * 4;
+  L.bias = o; o += (uint32_t)((C_out + 3) & ~3) * 4u;
+  L.cum_c = o; o += (kMaxUtt + 1) * 4;
+  L.cum_f = o; o += (kMaxUtt + 1) * 4;
+  L.list_c = o; o += kListCap * 4;
+  L.list_cf = o; o += kListCap * 4;
+  L.list_f = o; o += kListCap * 4;
+  o = (o + 7u) & ~7u;
+  L.bars = o; o += 32 * 8;
+  L.tmem_slot = o; o += 16;
+  L.total = o;
+  return L;
+}
+
+struct WsArgs {
+  SepArgs s;
+  int32_t B, n_tiles, n_split;
+  long long* trace;   // development aid (tools/ws_trace.py): per-role (tag, globaltimer) log of CTA 0, or null
+};
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define WS_TRACE(role, tag)                                                            \
+  do {                                                                                 \
+    if (wa.trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_n < 250) {        \
+      wa.trace[(role) * 512 + 2 * trace_n] = (tag);                                    \
+      wa.trace[(role) * 512 + 2 * trace_n + 1] = gtime();                              \
+      ++trace_n;                                                                       \
+    }                                                                                  \
+  } while (0)
+
+template <int CIN, int ACT>
+__global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const WsArgs wa) {
+  const SepArgs& a = wa.s;
+  const int C_in = CIN ? CIN : a.C_in;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  unsigned char* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NT = a.NT;
+  const uint32_t bBytes = (uint32_t)NT * 128u;
+  const WsLayout L = ws_layout(NT, a.C_out);
+  const long long t_entry = (wa.trace != nullptr) ? gtime() : 0;
+
+  unsigned char* sA = sm + L.a;
+  float* sBias = reinterpret_cast<float*>(sm + L.bias);
+  int32_t* cum_c = reinterpret_cast<int32_t*>(sm + L.cum_c);
+  int32_t* cum_f = reinterpret_cast<int32_t*>(sm + L.cum_f);
+  int32_t* list_c = reinterpret_cast<int32_t*>(sm + L.list_c);
+  int32_t* list_cf = reinterpret_cast<int32_t*>(sm + L.list_cf);   // cf of each compute item (rows 2t >= cf are padding)
+  int32_t* list_f = reinterpret_cast<int32_t*>(sm + L.list_f);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem_slot);
+  const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sm + L.b), bar_u = smem_u32(sm + L.bars);
+  // barriers: A full (one arrival per depthwise warp) / A empty (commit), B full (tx) / B empty (commit),
+  //           accumulator full (commit) / accumulator empty (one arrival per epilogue warp)
+  auto bar_afull = [&](int s) { return bar_u + 8u * (uint32_t)s; };
+  auto bar_aempty = [&](int s) { return bar_u + 8u * (uint32_t)(kStagesA + s); };
+  auto bar_bfull = [&](int s) { return bar_u + 8u * (uint32_t)(2 * kStagesA + s); };
+  auto bar_bempty = [&](int s) { return bar_u + 8u * (uint32_t)(2 * kStagesA + kStagesB + s); };
+  auto bar_accf = [&](int i) { return bar_u + 8u * (uint32_t)(2 * kStagesA + 2 * kStagesB + i); };
+  auto bar_acce = [&](int i) { return bar_u + 8u * (uint32_t)(2 * kStagesA + 2 * kStagesB + 2 + i); };
+
+  // ---- prologue: TMEM, barriers, bias, work lists ---------------------------------------------------
+  if (warp == kDwWarps + kEpWarps + 1) tmem_alloc(smem_u32(tmem_slot), kTmemColsWs);
+  if (tid == 0) {
+    for (int s = 0; s < kStagesA; ++s) {
+      mbar_init(bar_afull(s), kDwWarps);
+      mbar_init(bar_aempty(s), 1);
+    }
+    for (int s = 0; s < kStagesB; ++s) {
+      mbar_init(bar_bfull(s), 1);
+      mbar_init(bar_bempty(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_accf(i), 1);
+      mbar_init(bar_acce(i), kEpWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < a.C_out; i += kWsThreads) sBias[i] = a.bias[i];
+  // per utterance: tiles that must be computed (receptive field reaches real data) and tiles that are padding
+  for (int u = tid; u < wa.B; u += kWsThreads) {
+    int ct = wa.n_tiles;
+    if (a.len0 != nullptr) {
+      const int cf = (max(a.len0[u], 0) + (1 << a.shift) - 1) >> a.shift;
+      ct = min(wa.n_tiles, (cf + 2 * kMT - 1) / (2 * kMT));      // tiles t0 with 2*t0 < cf
+    }
+    cum_c[u + 1] = ct * wa.n_split;
+    cum_f[u + 1] = wa.n_tiles - ct;
+  }
+  __syncthreads();
+  if (warp == 0) {   // inclusive scans of the two count arrays (B <= 1024: 32 steps of a 32-wide scan)
+    int carry_c = 0, carry_f = 0;
+    for (int base = 0; base < wa.B; base += 32) {
+      const int u = base + lane;
+      int vc = (u < wa.B) ? cum_c[u + 1] : 0, vf = (u < wa.B) ? cum_f[u + 1] : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int c2 = __shfl_up_sync(0xffffffffu, vc, d), f2 = __shfl_up_sync(0xffffffffu, vf, d);
+        if (lane >= d) { vc += c2; vf += f2; }
+      }
+      if (u < wa.B) { cum_c[u + 1] = carry_c + vc; cum_f[u + 1] = carry_f + vf; }
+      carry_c += __shfl_sync(0xffffffffu, vc, 31);
+      carry_f += __shfl_sync(0xffffffffu, vf, 31);
+    }
+    if (lane == 0) { cum_c[0] = 0; cum_f[0] = 0; }
+  }
+  __syncthreads();
+  const int total_c = cum_c[wa.B], total_f = cum_f[wa.B];
+  const int G = (int)gridDim.x, me = (int)blockIdx.x;
+  const int n_c = (total_c > me) ? (total_c - me - 1) / G + 1 : 0;   // <= kListCap (checked by the host)
+  const int n_f = (total_f > me) ? (total_f - me - 1) / G + 1 : 0;
+  auto find = [&](const int32_t* cum, int x) -> int {   // largest u in [0,B) with cum[u] <= x
+    int lo = 0, hi = wa.B;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (cum[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+  };
+  for (int k = tid; k < n_c; k += kWsThreads) {
+    const int j = me + k * G;
+    const int u = find(cum_c, j);
+    const int r = j - cum_c[u];
+    const int tile = r / wa.n_split, nh = r - tile * wa.n_split;
+    list_c[k] = (u << 16) | (tile << 4) | nh;
+    list_cf[k] = (a.len0 != nullptr) ? ((max(a.len0[u], 0) + (1 << a.shift) - 1) >> a.shift) : 0x7fffffff;
+  }
+  for (int k = tid; k < n_f; k += kWsThreads) {
+    const int j = me + k * G;
+    const int u = find(cum_f, j);
+    const int ct = (cum_c[u + 1] - cum_c[u]) / wa.n_split;
+    list_f[k] = (u << 16) | (ct + (j - cum_f[u]));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (wa.trace != nullptr && blockIdx.x == 0 && tid == 0) { wa.trace[5 * 512] = 1; wa.trace[5 * 512 + 1] = gtime(); wa.trace[5 * 512 + 2] = n_c; wa.trace[5 * 512 + 3] = n_f; wa.trace[5 * 512 + 4] = t_entry; }
+  const uint32_t tmem = *tmem_slot;
+  const int n_chunks = a.n_chunks;
+  int trace_n = 0;
+
+  if (warp < kDwWarps) {
+    // =========================== depthwise producers ===========================================
+    // Warp 0 pulls the NEXT tile's whole input window (263 consecutive rows, contiguous in memory) into L2
+    // with bulk prefetches while this tile is being reduced, so the loads below see L2 latency.
+    auto prefetch_tile = [&](int k) {
+      if (warp != 0 || k >= n_c) return;
+      const int item = list_c[k];
+      const int b = item >> 16, t0 = ((item >> 4) & 0xfff) * kMT;
+      const int rows = min(2 * (kMT - 1) + 9, a.T_in - 2 * t0);
+      if (rows <= 0) return;
+      const char* base = reinterpret_cast<const char*>(a.x + ((size_t)b * a.T_in + 2 * t0) * C_in);
+      const long long bytes = (long long)rows * C_in * 4;
+      for (long long off = (long long)lane * 16384; off < bytes; off += 32ll * 16384) {
+        const uint32_t sz = (uint32_t)min(16384ll, bytes - off);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(sz) : "memory");
+      }
+    };
+    prefetch_tile(1);
+    int g = 0;
+    for (int k = 0; k < n_c; ++k) {
+      if (k > 0) prefetch_tile(k + 1);
+      const int item = list_c[k];
+      const int b = item >> 16, t0 = ((item >> 4) & 0xfff) * kMT;
+      const int r0 = 2 * (t0 + warp * kRunWs);   // first input row of this warp's run
+      const float* xrow = a.x + ((size_t)b * a.T_in + r0) * C_in + lane;
+      const bool run_inside = (r0 + kWinWs <= a.T_in);
+      const bool run_needed = (r0 < list_cf[k]);  // a run that starts in the padding only yields the constant row
+      for (int kc = 0; kc < n_chunks; ++kc, ++g) {
+        const int s = g % kStagesA, n = g / kStagesA;
+        float v[kWinWs];
+        float w[9];
+        if (run_needed) {
+          const int c0 = kc * kKC;
+          const int kvalid = min(kKC, C_in - c0);
+          const bool cok = lane < kvalid;
+          if (run_inside && kvalid == kKC) {   // common case: unpredicated loads at immediate offsets
+            const float* xp = xrow + c0;
+#pragma unroll
+            for (int i = 0; i < kWinWs; ++i) v[i] = __ldg(xp + i * C_in);
+#pragma unroll
+            for (int kk = 0; kk < 9; ++kk) w[kk] = __ldg(a.dw + kk * C_in + c0 + lane);
+          } else {
+#pragma unroll
+            for (int i = 0; i < kWinWs; ++i)
+              v[i] = (cok && r0 + i < a.T_in) ? __ldg(xrow + c0 + (size_t)i * C_in) : 0.0f;
+#pragma unroll
+            for (int kk = 0; kk < 9; ++kk) w[kk] = cok ? __ldg(a.dw + kk * C_in + c0 + lane) : 0.0f;
+          }
+        }
+        if (n > 0) mbar_wait(bar_aempty(s), (n - 1) & 1);   // (the loads above are already in flight)
+        if (warp == 0 || warp == 15) WS_TRACE(warp == 0 ? 0 : 1, 100 + kc);
+        if (run_needed) {
+          unsigned char* As = sA + s * kABytes;
+#pragma unroll
+          for (int j = 0; j < kRunWs; ++j) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int kk = 0; kk < 9; ++kk) acc = fmaf(v[2 * j + kk], w[kk], acc);
+            const int row = warp * kRunWs + j;
+            const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u;
+            *reinterpret_cast<uint32_t*>(As + off) = to_tf32(acc);
+          }
+        }
+        fence_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_afull(s));
+        if (warp == 0 || warp == 15) WS_TRACE(warp == 0 ? 0 : 1, 200 + kc);
+      }
+    }
+  } else if (warp < kDwWarps + kEpWarps) {
+    // =========================== epilogue + padding fill ========================================
+    const int e = warp - kDwWarps;
+    const int q = e & 3, half = e >> 2;      // TMEM lane quadrant (= warp id % 4), column-group parity
+    float* stg = reinterpret_cast<float*>(sm + L.stg) + e * (32 * kStgStride);
+    const int ngroups = NT >> 5;
+    const int q4 = a.C_out >> 2;
+    int fdone = 0;
+    auto do_fill = [&](int upto) {           // padding tiles: whole rows of the constant padding row
+      for (; fdone < upto; ++fdone) {
+        const int item = list_f[fdone];
+        const int b = item >> 16, t0 = (item & 0xffff) * kMT;
+        const int rows = min(kMT, a.T_out - t0);
+        float* dst = a.y + ((size_t)b * a.T_out + t0) * a.C_out;
+        const float4* pr = reinterpret_cast<const float4*>(a.pad_out);
+        for (int c4 = lane; c4 < q4; c4 += 32) {
+          const float4 pv = __ldg(pr + c4);
+          for (int r = e; r < rows; r += kEpWarps) *reinterpret_cast<float4*>(dst + (size_t)r * a.C_out + 4 * c4) = pv;
+        }
+      }
+    };
+    for (int k = 0; k < n_c; ++k) {
+      const int item = list_c[k];
+      const int b = item >> 16, t0 = ((item >> 4) & 0xfff) * kMT, n0 = (item & 0xf) * NT;
+      const int cf = list_cf[k];
+      const int acc = k & 1;
+      if (e == 0 || e == 7) WS_TRACE(e == 0 ? 3 : 4, 300);
+      mbar_wait(bar_accf(acc), (k >> 1) & 1);
+      tc_fence_after();
+      if (e == 0 || e == 7) WS_TRACE(e == 0 ? 3 : 4, 301);
+      for (int g = half; g < ngroups; g += 2) {
+        uint32_t r[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + g * 32), r);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bv = *reinterpret_cast<const float4*>(sBias + n0 + g * 32 + 4 * i);
+          float4 o;
+          o.x = act_apply<ACT>(__uint_as_float(r[4 * i + 0]) + bv.x);
+          o.y = act_apply<ACT>(__uint_as_float(r[4 * i + 1]) + bv.y);
+          o.z = act_apply<ACT>(__uint_as_float(r[4 * i + 2]) + bv.z);
+          o.w = act_apply<ACT>(__uint_as_float(r[4 * i + 3]) + bv.w);
+          *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * i) = o;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = (lane >> 3) + 4 * i;
+          const int c4 = (lane & 7) * 4;
+          float4 o = *reinterpret_cast<const float4*>(stg + rr * kStgStride + c4);
+          const int t = t0 + q * 32 + rr;
+          if (2 * t >= cf) o = __ldg(reinterpret_cast<const float4*>(a.pad_out + n0 + g * 32 + c4));
+          if (t < a.T_out)
+            *reinterpret_cast<float4*>(a.y + ((size_t)b * a.T_out + t) * a.C_out + n0 + g * 32 + c4) = o;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce(acc));   // this warp has read its part of the accumulator
+      if (e == 0 || e == 7) WS_TRACE(e == 0 ? 3 : 4, 302);
+      do_fill((int)(((long long)n_f * (k + 1)) / n_c));
+      if (e == 0 || e == 7) WS_TRACE(e == 0 ? 3 : 4, 303);
+    }
+    do_fill(n_f);
+    if (e == 0 || e == 7) WS_TRACE(e == 0 ? 3 : 4, 304);
+  } else if (warp == kDwWarps + kEpWarps) {
+    // =========================== B loader ========================================================
+    if (lane == 0) {
+      int g = 0;
+      for (int k = 0; k < n_c; ++k) {
+        const int nh = list_c[k] & 0xf;
+        const float* bsrc = a.bpack + (size_t)nh * n_chunks * NT * kKC;
+        for (int kc = 0; kc < n_chunks; ++kc, ++g) {
+          const int s = g % kStagesB, n = g / kStagesB;
+          if (n > 0) mbar_wait(bar_bempty(s), (n - 1) & 1);
+          mbar_expect_tx(bar_bfull(s), bBytes);
+          bulk_g2s(sB_u + s * bBytes, bsrc + (size_t)kc * NT * kKC, bBytes, bar_bfull(s));
+        }
+      }
+    }
+  } else {
+    // =========================== MMA issuer ======================================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(kMT, NT);
+      int g = 0;
+      for (int k = 0; k < n_c; ++k) {
+        const int acc = k & 1;
+        if (k >= 2) {                        // the epilogue has drained this accumulator (tile k-2)
+          mbar_wait(bar_acce(acc), ((k >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t d_tmem = tmem + (uint32_t)(acc * NT);
+        for (int kc = 0; kc < n_chunks; ++kc, ++g) {
+          const int sa = g % kStagesA, na = g / kStagesA, sb = g % kStagesB, nb = g / kStagesB;
+          mbar_wait(bar_afull(sa), na & 1);
+          WS_TRACE(2, 400 + kc);
+          mbar_wait(bar_bfull(sb), nb & 1);
+          tc_fence_after();
+          WS_TRACE(2, 500 + kc);
+          const uint64_t da = umma_desc_sw128(sA_u + sa * kABytes);
+          const uint64_t db = umma_desc_sw128(sB_u + sb * bBytes);
+          const int ksteps = min(kKC, C_in - kc * kKC) >> 3;
+          for (int kk = 0; kk < ksteps; ++kk)
+            umma_tf32(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc, (kc | kk) != 0 ? 1u : 0u);
+          umma_commit(bar_aempty(sa));
+          umma_commit(bar_bempty(sb));
+        }
+        umma_commit(bar_accf(acc));
+        WS_TRACE(2, 600);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wa.trace != nullptr && blockIdx.x == 0 && tid == 0) wa.trace[5 * 512 + 5] = gtime();
+  if (warp == kDwWarps + kEpWarps + 1) tmem_dealloc(tmem, kTmemColsWs);
+}
+
+typedef void (*WsKernel)(const WsArgs);
+template <int CIN>
+WsKernel pick_act_ws(int act) {
+  switch (act) {
+    case TASR_ACT_TANH: return sepconv_ws_kernel<CIN, TASR_ACT_TANH>;
+    case TASR_ACT_GELU_ERF: return sepconv_ws_kernel<CIN, TASR_ACT_GELU_ERF>;
+    case TASR_ACT_RELU: return sepconv_ws_kernel<CIN, TASR_ACT_RELU>;
+    default: return sepconv_ws_kernel<CIN, TASR_ACT_NONE>;
+  }
+}
+WsKernel pick_kernel_ws(int c_in, int act) {
+  switch (c_in) {
+    case 80: return pick_act_ws<80>(act);
+    case 192: return pick_act_ws<192>(act);
+    case 384: return pick_act_ws<384>(act);
+    default: return pick_act_ws<0>(act);
+  }
+}
+
+}  // namespace
+
+static long long* g_ws_trace = nullptr;
+// Development aid: a device buffer of 6*512 int64 that CTA 0 of the next launches logs (tag, ns) pairs into.
+extern "C" void tasr_debug_ws_trace(long long* dev_buf) { g_ws_trace = dev_buf; }
+
+// Returns TASR_OK after launching, or a negative value when this shape is not handled by the persistent
+// kernel (the caller then uses sepconv_tf32_kernel).
+int tasr_sepconv_ws_launch(const TasrSepConvPlan* p, const SepArgs& sa, int32_t B, cudaStream_t st) {
+  const int n_tiles = (sa.T_out + kMT - 1) / kMT;
+  if (B > kMaxUtt || n_tiles > 0xfff || p->n_split > 15 || 2 * p->NT > kTmemColsWs) return -1;
+  const int grid = sm_count();
+  const long long dense = (long long)B * n_tiles * p->n_split;
+  if ((dense + grid - 1) / grid > kListCap) return -1;
+  const WsLayout L = ws_layout(p->NT, p->L.c_out);
+  const size_t smem = (size_t)L.total + 1024;
+  if (smem > 227 * 1024) return -1;
+  WsKernel kern = pick_kernel_ws(p->L.c_in, p->L.activation);
+  TASR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  WsArgs wa;
+  wa.s = sa; wa.B = B; wa.n_tiles = n_tiles; wa.n_split = p->n_split;
+  wa.trace = g_ws_trace;
+  const int g = (int)(dense < grid ? (dense > 0 ? dense : 1) : grid);
+  kern<<<g, kWsThreads, smem, st>>>(wa);
+  TASR_LAUNCH_CHECK("sepconv_ws_kernel");
+  return TASR_OK;
+}

@@ -523,3 +523,27 @@ def test_featurizer_waveform_mode(cuda_device):
         assert not out[b, L:].any()
     one = f(gpu(wav[0, :16000].copy(), cuda_device)).cpu().numpy()
     np.testing.assert_array_equal(one, out[0, :16000])
+
+
+def test_sepconv_persistent_kernel_matches_per_tile_kernel_bitwise(cuda_device, monkeypatch):
+    """csrc/sepconv_ws.cu (persistent, warp-specialised; opt-in with TASR_SEPCONV_WS=1) and
+    csrc/sepconv_tf32.cu (one CTA per tile; the default) do the same arithmetic in the same order:
+    identical bits, dense and ragged."""
+    from telugu_asr_b200.synth import draw_lengths
+    lens = draw_lengths(40, 1600, 240000, seed=13)
+    lens[1], lens[2] = 399, 240000
+    wav, ln = oracle.make_waveforms(lens, seed=13, dist="tilt")
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    feat = tasr.SpeechFeaturizer(**tasr.REFERENCE_SPEECH_CONFIG)
+    feats, nf = feat(gpu(wav, cuda_device), gpu(ln, cuda_device))
+    res = {}
+    for ws in ("1", "0"):
+        monkeypatch.setenv("TASR_SEPCONV_WS", ws)
+        for ragged in (True, False):
+            layer = tasr.Conv1DSubsamplingLayer(192, tasr.REFERENCE_SUBSAMPLING_CONFIG, math="tf32", assume_zero_padding=ragged)
+            layer.set_weights(weights, cuda_device)
+            res[(ws, ragged)] = _call_or_skip(layer, feats, mask=nf)[0]
+    torch.cuda.synchronize()
+    base = res[("0", False)]
+    for key, val in res.items():
+        assert torch.equal(val, base), key
