@@ -13,7 +13,7 @@ import yaml
 from .speech_featurizer import SpeechFeaturizer
 from .subsampling import Conv1DSubsamplingLayer
 
-__all__ = ["FrontEnd", "REFERENCE_SPEECH_CONFIG", "REFERENCE_SUBSAMPLING_CONFIG", "load_reference_yaml"]
+__all__ = ["FrontEnd", "CapturedFrontEnd", "REFERENCE_SPEECH_CONFIG", "REFERENCE_SUBSAMPLING_CONFIG", "load_reference_yaml"]
 
 # config/model.yaml:1-17
 REFERENCE_SPEECH_CONFIG = dict(
@@ -67,3 +67,58 @@ class FrontEnd:
         if return_features:
             return out, mask, len3, feats, n_frames
         return out, mask, len3
+
+
+class CapturedFrontEnd:
+    """The whole step (peak -> log-mel -> 3x separable conv -> lengths/mask) captured once into a CUDA graph
+    for a fixed batch shape and replayed with one launch: the seven kernel launches of a step and the
+    allocator calls between them disappear from the host path, and the ~2 us inter-kernel gaps shrink.
+
+    Static shape contract: `wav` [batch, n_max] and `lengths` [batch] are device buffers owned by this object —
+    write the batch into them (e.g. `PackedBatch.unpack` can target them, or `load()` copies), then `replay()`.
+    Ragged batches are handled by the kernels themselves (they read `lengths` on the device), so one graph
+    serves every batch of that shape.  Outputs are static tensors too, padded for n_max: `encoder_input`
+    [batch, T3(n_max), d], `padding_mask` [batch, T3(n_max)], `len3` [batch]; the reference's mask width
+    max(len3) (encoder.py:44) is `mask_width(max_length)` columns of it."""
+
+    def __init__(self, frontend: FrontEnd, batch: int, n_max: int, device):
+        self.fe = frontend
+        self.device = torch.device(device)
+        self.n_max = -(-int(n_max) // 4) * 4
+        self.max_length = int(n_max)
+        with torch.cuda.device(self.device):
+            self.wav = torch.zeros((batch, self.n_max), dtype=torch.float32, device=self.device)
+            self.lengths = torch.zeros((batch,), dtype=torch.int32, device=self.device)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):           # warm-up outside capture: plans, attributes, table uploads
+                for _ in range(2):
+                    self.fe(self.wav, self.lengths, max_length=self.max_length)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            from . import _native
+            l0 = _native.lib().tasr_launch_count()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.encoder_input, self.padding_mask, self.len3 = self.fe(self.wav, self.lengths, max_length=self.max_length)
+            self.kernels_per_replay = int(_native.lib().tasr_launch_count() - l0)
+
+    def load(self, wav: torch.Tensor, lengths: torch.Tensor) -> None:
+        """Copy a [batch, <= n_max] device batch into the static input buffers (stream ordered)."""
+        self.wav[:, : wav.shape[1]].copy_(wav, non_blocking=True)
+        self.lengths.copy_(lengths.to(torch.int32), non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.encoder_input, self.padding_mask, self.len3
+
+    __call__ = replay
+
+    def mask_width(self, max_length: int) -> int:
+        """max(len3) for a batch whose longest utterance has `max_length` samples (host arithmetic)."""
+        from .subsampling import get_conv_length
+        w = max(0, int(self.fe.featurizer.get_nframes(int(max_length))))
+        sub = self.fe.subsampling
+        for i in range(len(sub.kernel_size)):
+            w = get_conv_length(w, sub.kernel_size[i], sub.padding[i], sub.strides[i])
+        return max(w, 0)

@@ -547,3 +547,26 @@ def test_sepconv_persistent_kernel_matches_per_tile_kernel_bitwise(cuda_device, 
     base = res[("0", False)]
     for key, val in res.items():
         assert torch.equal(val, base), key
+
+
+def test_cuda_graph_replay_matches_eager_bitwise(cuda_device):
+    """CapturedFrontEnd: the step captured into a CUDA graph for a fixed [B, N_max]; replays on different
+    ragged batches of that shape give exactly the eager results."""
+    from telugu_asr_b200.synth import draw_lengths
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    fe = tasr.FrontEnd(math="tf32")
+    fe.set_weights(weights, cuda_device)
+    n_max = 48000
+    cap = tasr.CapturedFrontEnd(fe, 12, n_max, cuda_device)
+    assert cap.kernels_per_replay >= 5
+    for seed in (1, 2):
+        lens = draw_lengths(12, 300, n_max, seed=seed, first_is_max=(seed == 1))
+        wav, ln = oracle.make_waveforms(lens, seed=seed, dist="tilt", n_max=n_max)
+        w, l = gpu(wav, cuda_device), gpu(ln, cuda_device)
+        cap.load(w, l)
+        enc, mask, len3 = cap.replay()
+        torch.cuda.synchronize()
+        ref_enc, ref_mask, ref_len3 = fe(w, l, max_length=n_max)
+        assert torch.equal(enc, ref_enc) and torch.equal(mask, ref_mask) and torch.equal(len3, ref_len3)
+        wdt = cap.mask_width(int(ln.max()))
+        assert wdt == int(ref_len3.max()) and not mask[:, wdt:].any()
