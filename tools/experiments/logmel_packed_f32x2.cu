@@ -1,0 +1,604 @@
+// EXPERIMENT (not built): logmel.cu with the FFT core in packed FP32x2 arithmetic (sm_100a FADD2/FMUL2/FFMA2).
+//
+// Two frames (f, f+16) share every 64-bit register of a half-warp's 256-point FFT, so each add, twiddle,
+// window, split and power instruction serves two frames; the staged samples are stored as (y[n], y[n+2560])
+// pairs and the P rows live inside the per-pair transpose scratch.  Measured on B200 / config 3
+// (profiles: gpurun_out/prof_lm4): warp instructions 98.0 M -> 68.0 M per launch (-31 %), issue utilisation
+// 61 % -> 40 %, FMA pipe 39 % -> 37 %, time 152 us -> 153.6 us — UNCHANGED.  FFMA2 issues in one slot but
+// occupies the FMA pipe for two cycles (tools/micro/f32x2_rate.cu: 35 T element-ops/s either way), and the
+// kernel is bound by per-warp latency chains at 16 resident warps per SM (shared memory caps it), not by issue
+// slots.  Kept for the record; parity was within tolerance on 'tilt' and marginally outside the 4x-float32-band
+// bound on one 'white' stress case.  To try it: copy over telugu_asr_b200/csrc/logmel.cu and rebuild.
+// Fused waveform -> log-mel kernel (sm_100a).
+//
+// Replaces, per utterance, src/speech_featurizer.py:136-161 (normalize_signal ->
+// preemphasis_signal -> tf.signal.stft(400/160, periodic Hann, rFFT-512) -> |X|^2 -> HTK mel
+// matmul -> log10(max(.,1e-9))) and the zero-padded collate of src/dataset.py:236-252.
+//
+// Work decomposition
+//   items = (a) the VALID 32-frame tiles of every utterance, dealt round-robin to the persistent
+//           CTAs (every CTA gets the same number of them +-1: a ragged batch stays balanced), and
+//           (b) the collate padding (rows t >= n_frames[b]), zero-filled in 128-row chunks that are
+//           dealt round-robin the same way, first, so the stores drain under the FFT work;
+//   tile  = 32 consecutive frames of one utterance (5360 samples, staged once in shared memory
+//           with gain and pre-emphasis applied in exactly the reference's float32 op order; the
+//           next tile's samples are prefetched into L2 while this one computes);
+//   FFT   = 16 lanes per frame (two frames per warp).  The 512-point real FFT is a 256-point
+//           complex FFT of z[m] = y[2m] + i*y[2m+1] done as 16x16: radix-16 in registers,
+//           twiddle, 16x16 transpose through a padded per-warp scratch, radix-16 again; then the
+//           real-FFT split, where lane t and lane 16-t exchange eight values by warp shuffle and
+//           each forms |X[k]|^2 and |X[256-k]|^2 for its eight k;
+//   mel   = lane <-> frame, warp <-> a contiguous group of mel bins.  For the config/model.yaml
+//           filterbank the sparsity structure is compiled in (mel_geometry.inc): every power bin
+//           is loaded once and feeds its two adjacent triangles with weights read straight from
+//           the kernel-parameter constant bank, fully unrolled (3 instructions per FFT bin).  Any
+//           other triangular filterbank takes the generic banded loop;
+//   out   = log, staged through shared memory, written with coalesced 128-bit stores.
+//
+// Per-lane constants (half-window, transpose twiddles) live in registers for the whole
+// persistent loop.  Twiddles are float64-derived tables.
+#include "common.cuh"
+
+using namespace tasr;
+
+namespace {
+
+#include "mel_geometry.inc"
+
+constexpr int kTileFrames = 32;
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kWavSmem = 5376;          // (32-1)*160+400 = 5360, +16 floats lanes 8..15 touch at m2=12
+constexpr int kPairShift = 16 * kFrameStep;              // 2560: frame f and frame f+16 are processed as one packed pair
+constexpr int kWpSlots = kWavSmem - kPairShift;          // 2816 packed (y[n], y[n+2560]) sample pairs
+constexpr int kWavSlots = (kWpSlots / 4 + kThreads - 1) / kThreads;   // groups of 4 pairs per thread (3; 704 = 2.75 * 256)
+constexpr int kScrStride = 17;          // complex-pair (16 B) units; odd -> conflict-free transposed reads
+constexpr int kScrPerPair = 16 * kScrStride * 4;          // floats per frame pair: 1088 (also holds the two P rows afterwards)
+constexpr int kPOffB = 560;             // P row of the pair's second frame inside the region (first: offset 0); + (pair index)
+constexpr int kOutStride = kMel + 1;    // 81
+constexpr int kPadChunkRows = 128;      // rows of collate padding zero-filled per work item
+constexpr int kChunkUtt = 1024;         // utterances whose work items are indexed at a time (4 per thread)
+
+struct __align__(16) Smem {
+  float wp[2 * kWpSlots];                  // packed staged samples; after the FFT phase: the [32][81] output staging tile
+  float scr[16 * kScrPerPair];             // per frame pair: 16x17 transpose scratch of complex pairs, then its two P rows
+  float2 twl[16 * 16];                     // twl[k2][t] = W256^(t*k2): the transpose twiddles, one row per k2
+  float2 hwin2[256];                       // 0.5*Hann, zero padded to 512, as (w[2m], w[2m+1])
+  float2 tw512[136];                       // W512^k, k = 0..128
+  int32_t vcum[kChunkUtt + 1];             // exclusive prefix of valid 32-frame tiles per utterance of the chunk
+  int32_t pcum[kChunkUtt + 1];             // exclusive prefix of 128-row padding chunks per utterance
+  int32_t wsum[2][kWarps];
+  int2 list[kThreads];                     // this CTA's next valid tiles: (utterance within chunk, tile index)
+  float4 band_w[kMelBandMaxW4];            // generic path only
+  MelBands bands;                          // generic path only
+};
+static_assert(sizeof(float) * kTileFrames * kOutStride <= sizeof(float) * 2 * kWpSlots, "output staging must fit in the sample buffer");
+static_assert(kPOffB + 15 + kBins + 4 <= kScrPerPair && 15 + kBins + 4 <= kPOffB, "both P rows must fit in a pair's scratch region");
+
+// Per-FFT-bin weights of the fixed-geometry mel projection, passed BY VALUE as a kernel parameter so
+// that they sit in the constant bank and FFMA reads them as operands (no load instruction):
+// wr[k] = W[k, seg(k)] (rising side of bin seg(k)), wf[k] = W[k, seg(k)-1] (falling side of the bin below).
+struct MelFixedW {
+  float wr[256];
+  float wf[256];
+};
+
+// ---- packed FP32x2 arithmetic (sm_100a FADD2 / FMUL2 / FFMA2) -------------------------------------------
+// One instruction works on two floats held in a 64-bit register pair; ptxas folds the pack/unpack moves
+// into register allocation and takes per-lane or constant scalars as broadcast operands.  The two halves
+// always belong to two different FRAMES (f and f+16) running the same FFT, so every operation of the
+// transform — adds, rotations by -i (a rename plus a sign), twiddles, window, split, power — is packed.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ u64 bc(float a) { return pk(a, a); }
+__device__ __forceinline__ void upk(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+struct c2 { u64 re, im; };   // one complex value of each of the two frames of a pair
+__device__ __forceinline__ c2 cadd(c2 a, c2 b) { return c2{add2(a.re, b.re), add2(a.im, b.im)}; }
+__device__ __forceinline__ c2 csub(c2 a, c2 b) { return c2{sub2(a.re, b.re), sub2(a.im, b.im)}; }
+// a * (wr + i wi) for a per-lane or constant scalar twiddle (both frames take the same twiddle)
+__device__ __forceinline__ c2 cmul(c2 a, float wr, float wi) {
+  return c2{fma2(a.re, bc(wr), mul2(a.im, bc(-wi))), fma2(a.re, bc(wi), mul2(a.im, bc(wr)))};
+}
+
+// Forward 4-point DFT in place (W4 = -i).
+__device__ __forceinline__ void fft4(c2& p0, c2& p1, c2& p2, c2& p3) {
+  const c2 s0 = cadd(p0, p2), s1 = csub(p0, p2), s2 = cadd(p1, p3), s3 = csub(p1, p3);
+  p0 = cadd(s0, s2);
+  p2 = csub(s0, s2);
+  p1 = c2{add2(s1.re, s3.im), sub2(s1.im, s3.re)};
+  p3 = c2{sub2(s1.re, s3.im), add2(s1.im, s3.re)};
+}
+
+// Forward 16-point DFT, radix 4x4, fully in registers.  Input natural order v[n]; on return
+// X[4c+d] is stored at v[c+4d]; use X16(v,k).
+__device__ __forceinline__ void fft16(c2 (&v)[16]) {
+  constexpr float C1 = 0.92387953251128675613f;  // cos(pi/8)
+  constexpr float S1 = 0.38268343236508977173f;  // sin(pi/8)
+  constexpr float H = 0.70710678118654752440f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) fft4(v[a], v[a + 4], v[a + 8], v[a + 12]);
+  // y[a][d] at v[a+4d]  *=  W16^(a*d),  W16^j = cos(j pi/8) - i sin(j pi/8)
+  v[1 + 4] = cmul(v[1 + 4], C1, -S1);                                                   // W^1
+  { const c2 x = v[1 + 8]; v[1 + 8] = c2{mul2(add2(x.re, x.im), bc(H)), mul2(sub2(x.im, x.re), bc(H))}; }     // W^2
+  v[1 + 12] = cmul(v[1 + 12], S1, -C1);                                                 // W^3
+  { const c2 x = v[2 + 4]; v[2 + 4] = c2{mul2(add2(x.re, x.im), bc(H)), mul2(sub2(x.im, x.re), bc(H))}; }     // W^2
+  { const c2 x = v[2 + 8]; v[2 + 8] = c2{x.im, sub2(0ull, x.re)}; }                      // W^4 = -i
+  { const c2 x = v[2 + 12]; v[2 + 12] = c2{mul2(sub2(x.im, x.re), bc(H)), mul2(add2(x.re, x.im), bc(-H))}; }  // W^6
+  v[3 + 4] = cmul(v[3 + 4], S1, -C1);                                                   // W^3
+  { const c2 x = v[3 + 8]; v[3 + 8] = c2{mul2(sub2(x.im, x.re), bc(H)), mul2(add2(x.re, x.im), bc(-H))}; }    // W^6
+  v[3 + 12] = cmul(v[3 + 12], -C1, S1);                                                 // W^9
+#pragma unroll
+  for (int d = 0; d < 4; ++d) fft4(v[4 * d], v[4 * d + 1], v[4 * d + 2], v[4 * d + 3]);
+}
+#define X16(v, k) (v)[((k) >> 2) + 4 * ((k) & 3)]
+
+__device__ __forceinline__ void st_global_v4(float* p, float4 v) {
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// log2 of a NORMAL positive float (the argument is clamped to output_floor >= FLT_MIN first, so the
+// denormal rescue sequence of __log2f is dead weight): one MUFU.
+__device__ __forceinline__ float lg2_normal(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+struct LogmelArgs {
+  const float* wav;
+  const int32_t* len;
+  const float* peak;       // may be null when !normalize
+  float* out;
+  int32_t* n_frames;
+  const float* hwin;
+  const float2* tw256;
+  const float2* tw512;
+  const float4* band_w;
+  const MelBands* bands;
+  int64_t row_stride;
+  int32_t B, T_max, tiles_per_row;
+  int32_t normalize;
+  int32_t pad_end;         // tf.signal.stft(pad_end=True): ceil(N/160) frames, the tail zero padded
+  int32_t mode;            // 0: mel projection + log; 1: log of the first 80 power bins ("spectrogram")
+  float preemph, floor_, log_scale;
+};
+
+__device__ __forceinline__ int frames_of(int n, const LogmelArgs& a) {   // src/speech_featurizer.py:163-166
+  const int Tb = a.pad_end ? (n > 0 ? (n + kFrameStep - 1) / kFrameStep : 0)
+                           : ((n >= kFrameLen) ? 1 + (n - kFrameLen) / kFrameStep : 0);
+  return min(Tb, a.T_max);
+}
+
+// ---- fixed-geometry mel projection (config/model.yaml filterbank), fully unrolled ------------------
+// Warp W owns mel bins [kMelGrp[W], kMelGrp[W+1]).  It walks segments m = first..last+1; in segment m
+// each power bin k is loaded once and accumulated into bin m (rising weight) and bin m-1 (falling
+// weight); bin m-1 is complete when segment m ends.  Summation is in ascending k, like a dot product.
+template <int M, int M0, int M1>
+struct MelSeg {
+  static __device__ __forceinline__ void run(const float* __restrict__ Prow, const MelFixedW& w, float* __restrict__ srow,
+                                             float floor_, float scale, float acc_prev) {
+    float acc_cur = 0.0f;
+    constexpr int kBegin = kMelSegStart[M], kEnd = kMelSegStart[M + 1];
+#pragma unroll
+    for (int k = kBegin; k < kEnd; ++k) {
+      const float p = Prow[k];
+      if (M < M1) acc_cur = fmaf(p, w.wr[k], acc_cur);
+      if (M > M0) acc_prev = fmaf(p, w.wf[k], acc_prev);
+    }
+    if (M > M0) srow[M - 1] = lg2_normal(fmaxf(acc_prev, floor_)) * scale;
+    if constexpr (M < M1) MelSeg<M + 1, M0, M1>::run(Prow, w, srow, floor_, scale, acc_cur);
+  }
+};
+
+template <int W>
+__device__ __forceinline__ void mel_fixed_group(const float* Prow, const MelFixedW& w, float* srow, float floor_, float scale) {
+  MelSeg<kMelGrp[W], kMelGrp[W], kMelGrp[W + 1]>::run(Prow, w, srow, floor_, scale, 0.0f);
+}
+
+template <bool FIXED>
+__global__ void __launch_bounds__(kThreads, 2)
+logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelFixedW mw) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t = lane & 15, half = lane >> 4;
+
+  // ---- n_frames (src/speech_featurizer.py:163-166) -------------------------------------------
+  for (int b = blockIdx.x * kThreads + tid; b < a.B; b += gridDim.x * kThreads) a.n_frames[b] = frames_of(a.len[b], a);
+
+  // ---- constant tables to shared memory ---------------------------------------------------------
+  for (int i = tid; i < 256; i += kThreads) {
+    S.twl[i] = a.tw256[((i & 15) * (i >> 4)) & 255];                       // [k2][t]
+    S.hwin2[i] = *reinterpret_cast<const float2*>(a.hwin + 2 * i);
+  }
+  const int partner = (lane & 16) | ((16 - t) & 15);
+
+  for (int i = tid; i <= 128; i += kThreads) S.tw512[i] = a.tw512[i];
+  if (!FIXED) {
+    for (int i = tid; i < kMelBandMaxW4; i += kThreads) S.band_w[i] = a.band_w[i];
+    const int32_t* src = reinterpret_cast<const int32_t*>(a.bands);
+    int32_t* dst = reinterpret_cast<int32_t*>(&S.bands);
+    for (int i = tid; i < (int)(sizeof(MelBands) / 4); i += kThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+
+  // Frame pair handled by this half-warp: frames pi and pi+16 of the tile, packed in the two halves of
+  // every 64-bit register.  Its scratch region holds the 16x17 transpose tile, then the two P rows
+  // (offsets chosen so that lane <-> frame reads in the mel phase hit 32 different banks).
+  const int pi = warp * 2 + half;
+  float* region = S.scr + pi * kScrPerPair;
+  float4* scr4 = reinterpret_cast<float4*>(region);
+  float* stage = S.wp;
+  const float2* twp = S.tw512 + t;           // W512^(t+16j) at twp[16j]; lane t=0 uses W512^128 for j=0
+  const int tw0 = (t == 0) ? 128 : 0;
+  const float* Pmel = S.scr + (lane & 15) * kScrPerPair + ((lane < 16) ? 0 : kPOffB) + (lane & 15);   // mel phase: lane <-> frame
+
+  // Work items are indexed per chunk of kChunkUtt utterances: two block-wide prefix sums (valid tiles,
+  // padding chunks) in shared memory, then item j -> (utterance, index) by binary search.  jv / jp are
+  // this CTA's next global item indices; they keep striding by gridDim.x across chunks.
+  int jv = blockIdx.x, jp = blockIdx.x, voff = 0, poff = 0;
+#pragma unroll 1
+  for (int cb = 0; cb < a.B; cb += kChunkUtt) {
+  const int nu = min(kChunkUtt, a.B - cb);
+  {
+    int vt[4], pt[4], vs = 0, ps = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int u = 4 * tid + i;
+      vt[i] = pt[i] = 0;
+      if (u < nu) {
+        vt[i] = (frames_of(a.len[cb + u], a) + kTileFrames - 1) / kTileFrames;
+        const int pad_rows = a.T_max - vt[i] * kTileFrames;
+        pt[i] = pad_rows > 0 ? (pad_rows + kPadChunkRows - 1) / kPadChunkRows : 0;
+      }
+      vs += vt[i]; ps += pt[i];
+    }
+    int vi = vs, pi = ps;   // inclusive scan over the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v2 = __shfl_up_sync(0xffffffffu, vi, d), p2 = __shfl_up_sync(0xffffffffu, pi, d);
+      if (lane >= d) { vi += v2; pi += p2; }
+    }
+    if (lane == 31) { S.wsum[0][warp] = vi; S.wsum[1][warp] = pi; }
+    __syncthreads();
+    int vb = vi - vs, pb = pi - ps;
+    for (int w = 0; w < warp; ++w) { vb += S.wsum[0][w]; pb += S.wsum[1][w]; }
+    if (tid == 0) { S.vcum[0] = 0; S.pcum[0] = 0; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      vb += vt[i]; pb += pt[i];
+      S.vcum[4 * tid + i + 1] = vb;
+      S.pcum[4 * tid + i + 1] = pb;
+    }
+    __syncthreads();
+  }
+  const int vtot = S.vcum[nu], ptot = S.pcum[nu];
+  auto find = [&](const int32_t* cum, int x) -> int {   // largest u in [0,nu) with cum[u] <= x
+    int lo = 0, hi = nu;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (cum[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+  };
+
+  // ---- (b) collate padding: rows beyond the last valid tile of every utterance, 128-row chunks ----
+  for (; jp < poff + ptot; jp += gridDim.x) {
+    const int u = find(S.pcum, jp - poff);
+    const int vt = S.vcum[u + 1] - S.vcum[u];
+    const int r0 = vt * kTileFrames + (jp - poff - S.pcum[u]) * kPadChunkRows;
+    const int rows = min(kPadChunkRows, a.T_max - r0);
+    float* dst = a.out + ((size_t)(cb + u) * a.T_max + r0) * kMel;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < rows * (kMel / 4); i += kThreads) st_global_v4(dst + 4 * i, z);
+  }
+
+  // ---- (a) valid tiles, round-robin ------------------------------------------------------------
+  // This CTA's tiles of the chunk are jv, jv+grid, ...; they are located once, one per thread, into a
+  // shared list (utterance, tile index) that the tile loop then just reads.
+#pragma unroll 1
+  while (jv < voff + vtot) {
+  const int nlist = min(kThreads, (voff + vtot - jv + (int)gridDim.x - 1) / (int)gridDim.x);
+  if (tid < nlist) {
+    const int x = jv - voff + tid * (int)gridDim.x;
+    const int u = find(S.vcum, x);
+    S.list[tid] = make_int2(u, x - S.vcum[u]);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int li = 0; li < nlist; ++li) {
+    const int2 item = S.list[li];
+    const int b = cb + item.x;
+    const int tf = item.y;
+
+    if (li + 1 < nlist && tid < 168) {  // next tile -> L2: 5360 samples = 167.5 lines of 128 B
+      const int2 nxt = S.list[li + 1];
+      const float* nrow = a.wav + (size_t)(cb + nxt.x) * a.row_stride;
+      const int ns = nxt.y * kTileFrames * kFrameStep + tid * 32;
+      if (ns < a.len[cb + nxt.x]) prefetch_l2(nrow + ns);
+    }
+
+    const int n = a.len[b];
+    const int Tb = frames_of(n, a);
+    const int f0 = tf * kTileFrames;
+    const int rows = min(kTileFrames, a.T_max - f0);
+    const int nvalid = min(kTileFrames, Tb - f0);   // >= 1: only valid tiles are enumerated
+    float* orow = a.out + ((size_t)b * a.T_max + f0) * kMel;
+
+    // ---- stage the tile: gain, pre-emphasis (reference float32 op order), to shared, packed ------
+    // wp[n] = (y[n], y[n + 2560]): sample n of frame f next to sample n of frame f+16.
+    {
+      const float* row = a.wav + (size_t)b * a.row_stride;
+      const int s0 = f0 * kFrameStep;
+      const int count = (nvalid - 1) * kFrameStep + kFrameLen;  // multiple of 4; s0+count <= n unless pad_end
+      const int lim = a.pad_end ? min(count, n - s0) : count;   // samples of the tile that exist
+      float g = 1.0f;
+      if (a.normalize) g = __fdiv_rn(1.0f, __fadd_rn(a.peak[b], 1e-9f));  // :70
+      const float c = a.preemph;
+      float4 x[2 * kWavSlots];
+      float xp[2 * kWavSlots];
+#pragma unroll
+      for (int u = 0; u < 2 * kWavSlots; ++u) {   // all loads first: 6 x 128-bit + 6 x 32-bit in flight per thread
+        const int i4 = tid + (u >> 1) * kThreads;
+        const int idx = 4 * i4 + (u & 1) * kPairShift;   // sample index inside the tile
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xp[u] = 0.0f;
+        if (i4 < kWpSlots / 4 && idx < lim) {
+          x[u] = *reinterpret_cast<const float4*>(row + s0 + idx);   // (rows are padded to 4 samples: in bounds)
+          if (s0 + idx > 0) xp[u] = row[s0 + idx - 1];
+        }
+      }
+      float4 y[2 * kWavSlots];
+#pragma unroll
+      for (int u = 0; u < 2 * kWavSlots; ++u) {
+        const int i4 = tid + (u >> 1) * kThreads;
+        const int idx = 4 * i4 + (u & 1) * kPairShift;
+        float4 v = x[u];
+        v.x = __fmul_rn(v.x, g); v.y = __fmul_rn(v.y, g); v.z = __fmul_rn(v.z, g); v.w = __fmul_rn(v.w, g);  // :71
+        y[u] = v;
+        if (c > 0.0f) {  // :75-79  y[0]=x[0]; y[n]=x[n]-c*x[n-1], product and difference rounded separately
+          const float vp = __fmul_rn(xp[u], g);
+          y[u].x = (s0 + idx > 0) ? __fsub_rn(v.x, __fmul_rn(c, vp)) : v.x;
+          y[u].y = __fsub_rn(v.y, __fmul_rn(c, v.x));
+          y[u].z = __fsub_rn(v.z, __fmul_rn(c, v.y));
+          y[u].w = __fsub_rn(v.w, __fmul_rn(c, v.z));
+        }
+        if (a.pad_end) {   // the zero padding is appended AFTER pre-emphasis (tf.signal.frame pads the signal it is given)
+          if (idx + 0 >= lim) y[u].x = 0.0f;
+          if (idx + 1 >= lim) y[u].y = 0.0f;
+          if (idx + 2 >= lim) y[u].z = 0.0f;
+          if (idx + 3 >= lim) y[u].w = 0.0f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kWavSlots; ++u) {
+        const int i4 = tid + u * kThreads;
+        if (i4 < kWpSlots / 4 && 4 * i4 < count + 16) {   // [count, count+16) must be finite zeros (window tail)
+          const float4 ya = y[2 * u], yb = y[2 * u + 1];
+          float4* dst = reinterpret_cast<float4*>(S.wp + 8 * i4);
+          dst[0] = make_float4(ya.x, yb.x, ya.y, yb.y);
+          dst[1] = make_float4(ya.z, yb.z, ya.w, yb.w);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- FFT + power: one frame pair per half-warp, both frames packed in FP32x2 registers ---------
+    // (a pair whose first frame is valid but whose second is not computes garbage in the second half of
+    //  every register: the halves never mix, and rows >= nvalid are never stored)
+    if (2 * warp < nvalid) {
+      const float4* frp = reinterpret_cast<const float4*>(S.wp) + (pi * kFrameStep) / 2 + t;
+      c2 v[16];
+#pragma unroll
+      for (int m2 = 0; m2 < 13; ++m2) {
+        const float4 sv = frp[16 * m2];                     // (yA[2m], yB[2m], yA[2m+1], yB[2m+1]), m = t + 16 m2
+        const float2 hw = S.hwin2[t + 16 * m2];
+        v[m2] = c2{mul2(pk(sv.x, sv.y), bc(hw.x)), mul2(pk(sv.z, sv.w), bc(hw.y))};
+      }
+      v[13] = v[14] = v[15] = c2{0ull, 0ull};
+      fft16(v);
+      // transpose twiddle W256^(t*k2) and scatter: scratch[k2][t]
+      __syncwarp();
+      {
+        float a0, a1, b0, b1;
+        upk(X16(v, 0).re, a0, a1); upk(X16(v, 0).im, b0, b1);
+        scr4[t] = make_float4(a0, a1, b0, b1);
+#pragma unroll
+        for (int k2 = 1; k2 < 16; ++k2) {
+          const float2 w = S.twl[k2 * 16 + t];
+          const c2 z = cmul(X16(v, k2), w.x, w.y);
+          upk(z.re, a0, a1); upk(z.im, b0, b1);
+          scr4[k2 * kScrStride + t] = make_float4(a0, a1, b0, b1);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const float4 q = scr4[t * kScrStride + n1];
+        v[n1] = c2{pk(q.x, q.y), pk(q.z, q.w)};
+      }
+      fft16(v);  // X16(v,k1) = Z[t + 16*k1] (half scaled)
+      __syncwarp();   // every lane has read its scratch row: the region now becomes the pair's two P rows
+
+      float* Pa = region + pi + t;              // frame pi:      P[k],     k = t + 16j
+      float* Pb = region + pi + 256 - t;        //                P[256-k]
+      // real-FFT split: pairs (k, 256-k), k = t+16j, j=0..7; partner lane holds Z[256-k] at k1=15-j
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        c2 za = X16(v, j);
+        const c2 zq = X16(v, 15 - j);
+        c2 zb = c2{__shfl_sync(0xffffffffu, zq.re, partner), __shfl_sync(0xffffffffu, zq.im, partner)};
+        if (t == 0) {  // residue 0 pairs with itself: (16j, 256-16j); slot j=0 takes the self-paired k=128
+          if (j == 0) { za = X16(v, 8); zb = za; }
+          else zb = X16(v, 16 - j);
+        }
+        const u64 er = add2(za.re, zb.re), ei = sub2(za.im, zb.im);      // E' = Z[k] + conj(Z[256-k])
+        const u64 dr = sub2(za.re, zb.re), di = add2(za.im, zb.im);      // D  = Z[k] - conj(Z[256-k])
+        const float2 wk = (j == 0) ? twp[tw0] : twp[16 * j];             // W512^k
+        // tt = W512^k * (-i*D) = (di + i(-dr)) * (wk.x + i wk.y)
+        const u64 ttr = fma2(di, bc(wk.x), mul2(dr, bc(wk.y)));
+        const u64 tti = fma2(di, bc(wk.y), mul2(dr, bc(-wk.x)));
+        const u64 ar = add2(er, ttr), ai = add2(ei, tti);                // X[k]
+        const u64 br = sub2(er, ttr), bi = sub2(ei, tti);                // conj(X[256-k])
+        const u64 pa = fma2(ar, ar, mul2(ai, ai)), pb = fma2(br, br, mul2(bi, bi));
+        float pa0, pa1, pb0, pb1;
+        upk(pa, pa0, pa1); upk(pb, pb0, pb1);
+        if (j == 0) {
+          const int ka = (t == 0) ? 128 : 0;                 // lane 0: k = 128 (both stores hit P[128])
+          Pa[ka] = pa0; Pa[kPOffB + ka] = pa1;
+          Pb[-ka] = pb0; Pb[kPOffB - ka] = pb1;
+        } else {
+          Pa[16 * j] = pa0; Pa[kPOffB + 16 * j] = pa1;
+          Pb[-16 * j] = pb0; Pb[kPOffB - 16 * j] = pb1;
+        }
+      }
+      if (t == 0) {
+        const c2 z0 = X16(v, 0);
+        const u64 p = mul2(add2(z0.re, z0.im), bc(2.0f)), q = mul2(sub2(z0.re, z0.im), bc(2.0f));
+        float p0, p1, q0, q1;
+        upk(mul2(p, p), p0, p1); upk(mul2(q, q), q0, q1);
+        Pa[0] = p0; Pa[kPOffB] = p1;
+        Pb[0] = q0; Pb[kPOffB] = q1;
+        if (!FIXED) {   // the generic banded loop may read up to four zero-weight columns past bin 256
+#pragma unroll
+          for (int z = 1; z <= 4; ++z) { Pb[z] = 0.0f; Pb[kPOffB + z] = 0.0f; }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- mel projection + log: lane = frame ---------------------------------------------------
+    {
+      const float* Prow = Pmel;
+      float* srow = stage + lane * kOutStride;
+      if (a.mode == 1) {   // "spectrogram": log power of the first 80 FFT bins (src/speech_featurizer.py:124-126)
+        for (int k = warp; k < kMel; k += kWarps) srow[k] = lg2_normal(fmaxf(Prow[k], a.floor_)) * a.log_scale;
+      } else if (FIXED) {
+        switch (warp) {
+          case 0: mel_fixed_group<0>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          case 1: mel_fixed_group<1>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          case 2: mel_fixed_group<2>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          case 3: mel_fixed_group<3>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          case 4: mel_fixed_group<4>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          case 5: mel_fixed_group<5>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          case 6: mel_fixed_group<6>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          default: mel_fixed_group<7>(Prow, mw, srow, a.floor_, a.log_scale); break;
+        }
+      } else {
+#pragma unroll 1
+        for (int m = warp; m < kMel; m += kWarps) {
+          const int k0 = S.bands.k0[m], n4 = S.bands.n4[m];
+          const float4* wp = S.band_w + S.bands.off4[m];
+          const float* pp = Prow + k0;
+          float acc = 0.0f;
+          for (int i = 0; i < n4; ++i) {
+            const float4 w = wp[i];
+            acc = fmaf(pp[4 * i + 0], w.x, acc);
+            acc = fmaf(pp[4 * i + 1], w.y, acc);
+            acc = fmaf(pp[4 * i + 2], w.z, acc);
+            acc = fmaf(pp[4 * i + 3], w.w, acc);
+          }
+          srow[m] = lg2_normal(fmaxf(acc, a.floor_)) * a.log_scale;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- coalesced store; rows beyond n_frames[b] inside this tile are the collate's 0.0 ---------
+    for (int i = tid; i < rows * (kMel / 4); i += kThreads) {
+      const int r = i / (kMel / 4), m4 = (i - r * (kMel / 4)) * 4;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nvalid) {
+        const float* sp = stage + r * kOutStride + m4;
+        o = make_float4(sp[0], sp[1], sp[2], sp[3]);
+      }
+      st_global_v4(orow + 4 * i, o);
+    }
+    __syncthreads();  // stage (= the sample buffer) and the scratch regions are reused by the next tile
+  }
+  jv += nlist * (int)gridDim.x;   // (the tile loop ends on a barrier, so the list can be rewritten)
+  }
+  voff += vtot; poff += ptot;
+  __syncthreads();   // the prefix tables are rebuilt for the next chunk
+  }
+}
+
+}  // namespace
+
+extern "C" int tasr_logmel_f32(const TasrFeaturizer* f, const float* wav, const int32_t* len,
+                               const float* peak, int32_t B, int64_t row_stride, float* out,
+                               int32_t T_max, int32_t* n_frames, tasr_stream_t stream) {
+  if (!f || !wav || !len || !out || !n_frames) return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32: null argument");
+  if (B < 0 || T_max < 0 || row_stride < 0) return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32: negative size");
+  if (f->p.normalize_signal && !peak)
+    return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32: normalize_signal is set but peak is NULL (run tasr_absmax_f32 first)");
+  if (!aligned16(wav) || (row_stride & 3) || !aligned16(out))
+    return fail(TASR_ERR_MISALIGNED, "tasr_logmel_f32: wav/out must be 16-byte aligned and row_stride a multiple of 4 samples");
+  if (f->p.feature_type == TASR_FEAT_WAVEFORM)
+    return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32: the handle's feature_type is 'waveform'; call tasr_waveform_f32");
+  if (B == 0) return TASR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0;
+  TASR_CUDA(cudaGetDevice(&dev));
+  if (dev != f->device) return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32: featurizer was created on device %d, current device is %d", f->device, dev);
+
+  const int tiles_per_row = (T_max + kTileFrames - 1) / kTileFrames;
+  const long long total = (long long)tiles_per_row * B;
+  if (total > 0x7fffffffLL) return fail(TASR_ERR_UNSUPPORTED, "tasr_logmel_f32: too many tiles");
+  static bool attr_set[64] = {false};
+  const size_t smem = sizeof(Smem);
+  if (dev < 64 && !attr_set[dev]) {
+    TASR_CUDA(cudaFuncSetAttribute(logmel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TASR_CUDA(cudaFuncSetAttribute(logmel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[dev] = true;
+  }
+  LogmelArgs a;
+  a.wav = wav; a.len = len; a.peak = peak; a.out = out; a.n_frames = n_frames;
+  a.hwin = f->d_hwin; a.tw256 = f->d_tw256; a.tw512 = f->d_tw512; a.band_w = f->d_band_w; a.bands = f->d_bands;
+  a.row_stride = row_stride; a.B = B; a.T_max = T_max; a.tiles_per_row = tiles_per_row;
+  a.normalize = f->p.normalize_signal ? 1 : 0;
+  a.pad_end = f->p.pad_end ? 1 : 0;
+  a.mode = (f->p.feature_type == TASR_FEAT_SPECTROGRAM) ? 1 : 0;
+  a.preemph = f->p.preemphasis; a.floor_ = f->p.output_floor; a.log_scale = f->log_scale;
+  // Persistent grid: two CTAs per SM; never more CTAs than work items (valid tiles + padding chunks <= total + B).
+  const long long cap = total + B;
+  const int grid = (int)((cap < (long long)2 * sm_count()) ? (cap > 0 ? cap : 1) : (long long)2 * sm_count());
+  if (f->mel_fixed) {
+    const MelFixedW* mw = reinterpret_cast<const MelFixedW*>(f->mel_fixed_w);
+    logmel_kernel<true><<<grid, kThreads, smem, st>>>(a, *mw);
+  } else {
+    static const MelFixedW zero_w = {};
+    logmel_kernel<false><<<grid, kThreads, smem, st>>>(a, zero_w);
+  }
+  TASR_LAUNCH_CHECK("logmel_kernel");
+  if (f->p.feature_type == TASR_FEAT_MFCC || f->p.normalize_zscore || f->p.normalize_min_max)
+    return tasr_feature_post_launch(f, out, n_frames, B, T_max, st);
+  return TASR_OK;
+}
+
+// Host side of the fixed-geometry check (called by tasr_featurizer_create): fills wr/wf from the dense
+// [257,80] matrix when its sparsity structure is the compiled-in one, else returns false.
+bool tasr_mel_fixed_from_dense(const float* mel_w_host, float* wr_wf_512) {
+  MelFixedW w = {};
+  if (kMelSegStart[0] != 1 || kMelSegStart[81] != 256) return false;
+  for (int k = 0; k < kBins; ++k) {
+    int j0 = -1, j1 = -1;
+    for (int m = 0; m < kMel; ++m)
+      if (mel_w_host[k * kMel + m] != 0.0f) { if (j0 < 0) j0 = m; j1 = m; }
+    if (k == 0 || k == 256) { if (j0 >= 0) return false; continue; }
+    if (j0 < 0 || j1 - j0 > 1) return false;
+    const int seg = j0 + 1;                                  // 1..80
+    if (!(k >= kMelSegStart[seg] && k < kMelSegStart[seg + 1])) return false;
+    w.wf[k] = mel_w_host[k * kMel + j0];
+    w.wr[k] = (seg < kMel) ? mel_w_host[k * kMel + seg] : 0.0f;
+  }
+  for (int k = 0; k < 256; ++k) { wr_wf_512[k] = w.wr[k]; wr_wf_512[256 + k] = w.wf[k]; }
+  return true;
+}
