@@ -27,6 +27,7 @@
 // Per-lane constants (half-window, transpose twiddles) live in registers for the whole
 // persistent loop.  Twiddles are float64-derived tables.
 #include "common.cuh"
+#include <stdlib.h>
 
 using namespace tasr;
 
@@ -507,7 +508,9 @@ extern "C" int tasr_logmel_f32(const TasrFeaturizer* f, const float* wav, const 
   a.preemph = f->p.preemphasis; a.floor_ = f->p.output_floor; a.log_scale = f->log_scale;
   // Persistent grid: two CTAs per SM; never more CTAs than work items (valid tiles + padding chunks <= total + B).
   const long long cap = total + B;
-  const int grid = (int)((cap < (long long)2 * sm_count()) ? (cap > 0 ? cap : 1) : (long long)2 * sm_count());
+  static const int ctas_per_sm = [] { const char* e = getenv("TASR_LOGMEL_CTAS_PER_SM"); const int v = e ? atoi(e) : 2; return v >= 1 && v <= 2 ? v : 2; }();
+  const long long full = (long long)ctas_per_sm * sm_count();
+  const int grid = (int)((cap < full) ? (cap > 0 ? cap : 1) : full);
   if (f->mel_fixed) {
     const MelFixedW* mw = reinterpret_cast<const MelFixedW*>(f->mel_fixed_w);
     logmel_kernel<true><<<grid, kThreads, smem, st>>>(a, *mw);
