@@ -6,58 +6,73 @@
 // its channel chunks in lock step (depthwise -> barrier -> MMA issue).  Here ONE CTA per SM lives for the
 // whole layer and its warps take roles:
 //
-//   warps 0-15  depthwise producers: lane <-> channel, a run of 8 output frames per warp, 23-row register
-//               sliding window straight from global memory (the next tile's window is pulled into L2 by
-//               cp.async.bulk.prefetch a tile ahead), result rounded to TF32 into a 3-deep A ring (UMMA
-//               K-major SWIZZLE_128B), mbarrier hand-off per stage — no CTA-wide barrier;
-//   warps 16-23 epilogue: tcgen05.ld -> +bias -> activation (SFU) -> per-warp transpose in shared memory ->
+//   warp 17     x loader: TMA tiled loads (cp.async.bulk.tensor.3d, tensor map over (C_in, T_in, B)) of each
+//               (tile, chunk) input window — 264 rows x 32 channels, out-of-range rows/channels zero-filled by
+//               the hardware — into a 3-deep shared ring, two chunks ahead of the arithmetic;
+//   warps 0-7   depthwise producers: lane <-> channel, a run of 16 output frames per warp from rows
+//               [32w, 32w+39) of the staged window (conflict-free 128-byte rows), result rounded to TF32 into
+//               a 2-deep A ring (UMMA K-major SWIZZLE_128B), mbarrier hand-off per stage — no CTA-wide barrier;
+//   warp 16     B loader: cp.async.bulk (TMA bulk copy) of the packed pw^T chunk into a 2-deep B ring;
+//   warp 18     MMA issuer: tcgen05.mma kind::tf32, M=128, N=NT, accumulators double-buffered in TMEM
+//               (2 x NT columns of the 512), tcgen05.commit frees ring stages and publishes accumulators;
+//   warps 8-15  epilogue: tcgen05.ld -> +bias -> activation (SFU) -> per-warp transpose in shared memory ->
 //               128-bit coalesced stores, overlapped with the next tile's main loop; they also write the
-//               constant padding rows of the ragged mode (tiles that lie entirely in the collate padding);
-//   warp 24     B loader: cp.async.bulk (TMA bulk copy) of the packed pw^T chunk into a 4-deep B ring;
-//   warp 25     MMA issuer: tcgen05.mma kind::tf32, M=128, N=NT, accumulators double-buffered in TMEM
-//               (2 x NT columns of the 512), tcgen05.commit frees ring stages and publishes accumulators.
+//               constant padding rows of the ragged mode (tiles that lie entirely in the collate padding).
 //
 // Work distribution: the tiles that need computing are enumerated through a block-wide prefix sum over the
 // utterances (ragged: ceil(cf/256) tiles per utterance, cf = ceil(n_frames / 2^layer)) and dealt round-robin
 // to the CTAs, so every SM gets the same number +-1; the padding tiles are dealt the same way.
 //
-// Status (round 1, B200, config 3): 66 / 89 / 75 us for the three layers against 67 / 98 / 72 us for the
-// per-tile kernel — no better.  A globaltimer trace of CTA 0 (tools/ws_trace.py) and ablations show a
-// cadence of ~0.9-1.2 us per 32-channel chunk that survives removing the depthwise loads, the depthwise
-// arithmetic, the B copies and the epilogue alike (the bare role/mbarrier/MMA skeleton alone takes
-// 29 / 41 / 37 us), i.e. the hand-offs between the roles, not bandwidth or arithmetic, pace the kernel.
-// Kept because it is bit-exact and is the starting point for round 2 (fewer, fatter hand-offs: K=64 or
-// K=96 per stage, one elected poller per warp, TMA-staged input tiles).
+// Status (round 1, B200, config 3): 62 / 82 / 63 us for the three layers against 62 / 94 / 68 us for the
+// per-tile kernel inside a step (369 vs 387 us per step on one stream; with two steps in flight on two
+// streams the difference shrinks to 347 vs 351 us, which is why it is not the default yet).  A globaltimer
+// trace of CTA 0 (tools/ws_trace.py) shows what paces it: a 32-channel chunk takes ~1.05 us in the depthwise
+// warps — ~0.2 us fetching the taps, ~0.1 us barrier wake-up, ~0.4 us window -> registers + hand-off,
+// ~0.45 us FMAs + TF32 store + proxy fence — all serial latency in two warps per scheduler, and a tile's
+// epilogue takes 6-9 us on its eight warps.  Earlier variants (per-lane LDG windows, cp.async windows,
+// 16 depthwise warps, K=64 per stage, deeper B ring) all landed within 5 % of the per-tile kernel.
 #include "sepconv_common.cuh"
+#include <cuda.h>
 
 using namespace tasr;
 using namespace tasr_sep;
 
 namespace {
 
-constexpr int kDwWarps = 16;
-constexpr int kRunWs = kMT / kDwWarps;          // 8 output frames per depthwise warp
-constexpr int kWinWs = 2 * (kRunWs - 1) + 9;    // 23 input rows per run
+constexpr int kDwWarps = 8;
+constexpr int kRunWs = kMT / kDwWarps;          // 16 output frames per depthwise warp
+constexpr int kWinWs = 2 * (kRunWs - 1) + 9;    // 39 input rows per run
 constexpr int kEpWarps = 8;
-constexpr int kWsThreads = (kDwWarps + kEpWarps + 2) * 32;   // 576
-constexpr int kStagesA = 3;   // depthwise -> MMA ring (16 KB each)
-constexpr int kStagesB = 4;   // pw^T chunk ring (NT*128 B each): deep enough to cover the L2 -> shared latency of the bulk copies
-constexpr int kMaxUtt = 1024;     // utterances indexed in shared memory
+constexpr int kWsThreads = (kDwWarps + kEpWarps + 3) * 32;   // 608: + B loader, x loader, MMA issuer
+constexpr int kStagesA = 2;   // depthwise -> MMA ring (16 KB each)
+constexpr int kStagesB = 2;   // pw^T chunk ring (NT*128 B each)
+constexpr int kStagesX = 3;   // input-tile ring: 264 rows x 32 channels fetched by TMA two chunks ahead of the arithmetic
+constexpr int kXRows = 264;   // 2*(128-1)+9 = 263 rows per 128-frame tile, fetched as boxes of 256 + 8 rows
+constexpr int kXBytes = kXRows * kKC * 4;
+constexpr int kMaxUtt = 512;      // utterances indexed in shared memory
 constexpr int kListCap = 256;    // work items per CTA
 constexpr int kTmemColsWs = 512;
+
+// TMA tiled load of a 3-D box (coordinates: channel, row, utterance) onto an mbarrier; out-of-range rows and
+// channels arrive as zeros.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 struct WsLayout {
-  uint32_t a, b, stg, bias, cum_c, cum_f, list_c, list_cf, list_f, bars, tmem_slot, total;
+  uint32_t a, b, xs, stg, bias, cum_c, cum_f, list_c, list_cf, list_f, bars, tmem_slot, total;
 };
 __host__ __device__ inline WsLayout ws_layout(int NT, int C_out) {
   WsLayout L;
   uint32_t o = 0;
   L.a = o; o += kStagesA * kABytes;
   L.b = o; o += kStagesB * (uint32_t)NT * 128u;
+  L.xs = o; o += kStagesX * kXBytes;
   L.stg = o; o += kEpWarps * 32 * kStgStride * 4;
   L.bias = o; o += (uint32_t)((C_out + 3) & ~3) * 4u;
   L.cum_c = o; o += (kMaxUtt + 1) * 4;
@@ -73,6 +88,8 @@ __host__ __device__ inline WsLayout ws_layout(int NT, int C_out) {
 }
 
 struct WsArgs {
+  CUtensorMap tm_hi;   // x as (C_in, T_in, B) float32, box 32 channels x 256 rows
+  CUtensorMap tm_lo;   // same tensor, box 32 channels x 8 rows (rows 256..263 of a tile's window)
   SepArgs s;
   int32_t B, n_tiles, n_split;
   long long* trace;   // development aid (tools/ws_trace.py): per-role (tag, globaltimer) log of CTA 0, or null
@@ -93,7 +110,7 @@ __device__ __forceinline__ long long gtime() {
   } while (0)
 
 template <int CIN, int ACT>
-__global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const WsArgs wa) {
+__global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const __grid_constant__ WsArgs wa) {
   const SepArgs& a = wa.s;
   const int C_in = CIN ? CIN : a.C_in;
   extern __shared__ unsigned char smem_raw[];
@@ -122,9 +139,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const WsArgs 
   auto bar_bempty = [&](int s) { return bar_u + 8u * (uint32_t)(2 * kStagesA + kStagesB + s); };
   auto bar_accf = [&](int i) { return bar_u + 8u * (uint32_t)(2 * kStagesA + 2 * kStagesB + i); };
   auto bar_acce = [&](int i) { return bar_u + 8u * (uint32_t)(2 * kStagesA + 2 * kStagesB + 2 + i); };
+  auto bar_xfull = [&](int s) { return bar_u + 8u * (uint32_t)(2 * kStagesA + 2 * kStagesB + 4 + s); };
+  auto bar_xempty = [&](int s) { return bar_u + 8u * (uint32_t)(2 * kStagesA + 2 * kStagesB + 4 + kStagesX + s); };
+  const uint32_t sX_u = smem_u32(sm + L.xs);
+  constexpr int kWarpB = kDwWarps + kEpWarps, kWarpX = kWarpB + 1, kWarpMma = kWarpB + 2;
 
   // ---- prologue: TMEM, barriers, bias, work lists ---------------------------------------------------
-  if (warp == kDwWarps + kEpWarps + 1) tmem_alloc(smem_u32(tmem_slot), kTmemColsWs);
+  if (warp == kWarpMma) tmem_alloc(smem_u32(tmem_slot), kTmemColsWs);
   if (tid == 0) {
     for (int s = 0; s < kStagesA; ++s) {
       mbar_init(bar_afull(s), kDwWarps);
@@ -133,6 +154,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const WsArgs 
     for (int s = 0; s < kStagesB; ++s) {
       mbar_init(bar_bfull(s), 1);
       mbar_init(bar_bempty(s), 1);
+    }
+    for (int s = 0; s < kStagesX; ++s) {
+      mbar_init(bar_xfull(s), 1);
+      mbar_init(bar_xempty(s), kDwWarps);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_accf(i), 1);
@@ -205,55 +230,39 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const WsArgs 
 
   if (warp < kDwWarps) {
     // =========================== depthwise producers ===========================================
-    // Warp 0 pulls the NEXT tile's whole input window (263 consecutive rows, contiguous in memory) into L2
-    // with bulk prefetches while this tile is being reduced, so the loads below see L2 latency.
-    auto prefetch_tile = [&](int k) {
-      if (warp != 0 || k >= n_c) return;
-      const int item = list_c[k];
-      const int b = item >> 16, t0 = ((item >> 4) & 0xfff) * kMT;
-      const int rows = min(2 * (kMT - 1) + 9, a.T_in - 2 * t0);
-      if (rows <= 0) return;
-      const char* base = reinterpret_cast<const char*>(a.x + ((size_t)b * a.T_in + 2 * t0) * C_in);
-      const long long bytes = (long long)rows * C_in * 4;
-      for (long long off = (long long)lane * 16384; off < bytes; off += 32ll * 16384) {
-        const uint32_t sz = (uint32_t)min(16384ll, bytes - off);
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(sz) : "memory");
-      }
+    // The input window of every (tile, chunk) — 264 rows x 32 channels — is brought into the shared x ring by
+    // the TMA warp two chunks ahead; each warp reduces its run of 16 output frames from rows [32w, 32w+39)
+    // of it (lane <-> channel, conflict-free rows of 128 B) into the A ring.
+    const float* xs_f = reinterpret_cast<const float*>(sm + L.xs);
+    auto load_w = [&](float (&w)[9], int kc) {     // depthwise taps of chunk kc for this lane's channel
+      const int c0 = kc * kKC;
+      const bool cok = lane < min(kKC, C_in - c0);
+#pragma unroll
+      for (int kk = 0; kk < 9; ++kk) w[kk] = cok ? __ldg(a.dw + kk * C_in + c0 + lane) : 0.0f;
     };
-    prefetch_tile(1);
+    float w[9], wn[9];
+    if (n_c > 0) load_w(w, 0);
     int g = 0;
     for (int k = 0; k < n_c; ++k) {
-      if (k > 0) prefetch_tile(k + 1);
-      const int item = list_c[k];
-      const int b = item >> 16, t0 = ((item >> 4) & 0xfff) * kMT;
-      const int r0 = 2 * (t0 + warp * kRunWs);   // first input row of this warp's run
-      const float* xrow = a.x + ((size_t)b * a.T_in + r0) * C_in + lane;
-      const bool run_inside = (r0 + kWinWs <= a.T_in);
-      const bool run_needed = (r0 < list_cf[k]);  // a run that starts in the padding only yields the constant row
+      const int r0 = 2 * (((list_c[k] >> 4) & 0xfff) * kMT + warp * kRunWs);   // first input row of this warp's run
+      const bool run_needed = (r0 < list_cf[k]);   // a run that starts in the padding only yields the constant row
       for (int kc = 0; kc < n_chunks; ++kc, ++g) {
+        load_w(wn, (kc + 1 < n_chunks) ? kc + 1 : 0);           // next chunk's taps: one chunk of latency hiding
+        const int sx = g % kStagesX, nx = g / kStagesX;
         const int s = g % kStagesA, n = g / kStagesA;
+        if (warp == 0) WS_TRACE(0, 140 + kc);
+        mbar_wait(bar_xfull(sx), nx & 1);
+        if (warp == 0) WS_TRACE(0, 160 + kc);
         float v[kWinWs];
-        float w[9];
         if (run_needed) {
-          const int c0 = kc * kKC;
-          const int kvalid = min(kKC, C_in - c0);
-          const bool cok = lane < kvalid;
-          if (run_inside && kvalid == kKC) {   // common case: unpredicated loads at immediate offsets
-            const float* xp = xrow + c0;
+          const float* xw = xs_f + (size_t)sx * (kXBytes / 4) + (size_t)(2 * warp * kRunWs) * kKC + lane;
 #pragma unroll
-            for (int i = 0; i < kWinWs; ++i) v[i] = __ldg(xp + i * C_in);
-#pragma unroll
-            for (int kk = 0; kk < 9; ++kk) w[kk] = __ldg(a.dw + kk * C_in + c0 + lane);
-          } else {
-#pragma unroll
-            for (int i = 0; i < kWinWs; ++i)
-              v[i] = (cok && r0 + i < a.T_in) ? __ldg(xrow + c0 + (size_t)i * C_in) : 0.0f;
-#pragma unroll
-            for (int kk = 0; kk < 9; ++kk) w[kk] = cok ? __ldg(a.dw + kk * C_in + c0 + lane) : 0.0f;
-          }
+          for (int i = 0; i < kWinWs; ++i) v[i] = xw[i * kKC];
         }
-        if (n > 0) mbar_wait(bar_aempty(s), (n - 1) & 1);   // (the loads above are already in flight)
-        if (warp == 0 || warp == 15) WS_TRACE(warp == 0 ? 0 : 1, 100 + kc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_xempty(sx));            // this warp has its window in registers
+        if (n > 0) mbar_wait(bar_aempty(s), (n - 1) & 1);
+        if (warp == 0) WS_TRACE(0, 100 + kc);
         if (run_needed) {
           unsigned char* As = sA + s * kABytes;
 #pragma unroll
@@ -269,7 +278,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const WsArgs 
         fence_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_afull(s));
-        if (warp == 0 || warp == 15) WS_TRACE(warp == 0 ? 0 : 1, 200 + kc);
+        if (warp == 0) WS_TRACE(0, 200 + kc);
+#pragma unroll
+        for (int kk = 0; kk < 9; ++kk) w[kk] = wn[kk];
       }
     }
   } else if (warp < kDwWarps + kEpWarps) {
@@ -337,7 +348,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const WsArgs 
     }
     do_fill(n_f);
     if (e == 0 || e == 7) WS_TRACE(e == 0 ? 3 : 4, 304);
-  } else if (warp == kDwWarps + kEpWarps) {
+  } else if (warp == kWarpB) {
     // =========================== B loader ========================================================
     if (lane == 0) {
       int g = 0;
@@ -349,6 +360,24 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const WsArgs 
           if (n > 0) mbar_wait(bar_bempty(s), (n - 1) & 1);
           mbar_expect_tx(bar_bfull(s), bBytes);
           bulk_g2s(sB_u + s * bBytes, bsrc + (size_t)kc * NT * kKC, bBytes, bar_bfull(s));
+        }
+      }
+    }
+  } else if (warp == kWarpX) {
+    // =========================== x loader (TMA) ==================================================
+    if (lane == 0) {
+      int g = 0;
+      for (int k = 0; k < n_c; ++k) {
+        const int item = list_c[k];
+        const int b = item >> 16, row0 = 2 * ((item >> 4) & 0xfff) * kMT;
+        for (int kc = 0; kc < n_chunks; ++kc, ++g) {
+          const int s = g % kStagesX, n = g / kStagesX;
+          if (n > 0) mbar_wait(bar_xempty(s), (n - 1) & 1);
+          WS_TRACE(1, 800 + kc);
+          mbar_expect_tx(bar_xfull(s), (uint32_t)kXBytes);
+          const uint32_t dst = sX_u + (uint32_t)s * kXBytes;
+          tma_load_3d(dst, &wa.tm_hi, kc * kKC, row0, b, bar_xfull(s));
+          tma_load_3d(dst + 256u * kKC * 4u, &wa.tm_lo, kc * kKC, row0 + 256, b, bar_xfull(s));
         }
       }
     }
@@ -387,7 +416,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const WsArgs 
   tc_fence_before();
   __syncthreads();
   if (wa.trace != nullptr && blockIdx.x == 0 && tid == 0) wa.trace[5 * 512 + 5] = gtime();
-  if (warp == kDwWarps + kEpWarps + 1) tmem_dealloc(tmem, kTmemColsWs);
+  if (warp == kWarpMma) tmem_dealloc(tmem, kTmemColsWs);
 }
 
 typedef void (*WsKernel)(const WsArgs);
@@ -411,6 +440,9 @@ WsKernel pick_kernel_ws(int c_in, int act) {
 
 }  // namespace
 
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static long long* g_ws_trace = nullptr;
 // Development aid: a device buffer of 6*512 int64 that CTA 0 of the next launches logs (tag, ns) pairs into.
 extern "C" void tasr_debug_ws_trace(long long* dev_buf) { g_ws_trace = dev_buf; }
@@ -429,6 +461,27 @@ int tasr_sepconv_ws_launch(const TasrSepConvPlan* p, const SepArgs& sa, int32_t 
   WsKernel kern = pick_kernel_ws(p->L.c_in, p->L.activation);
   TASR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   WsArgs wa;
+  {
+    static PFN_encodeTiled encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      TASR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      if (!fn || qres != cudaDriverEntryPointSuccess) return -1;
+      encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)p->L.c_in, (cuuint64_t)sa.T_in, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)p->L.c_in * 4, (cuuint64_t)sa.T_in * p->L.c_in * 4};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t box_hi[3] = {(cuuint32_t)kKC, 256, 1}, box_lo[3] = {(cuuint32_t)kKC, 8, 1};
+    CUresult r1 = encode(&wa.tm_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(sa.x), dims, strides, box_hi, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = encode(&wa.tm_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(sa.x), dims, strides, box_lo, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return -1;   // e.g. strides not multiples of 16 bytes: per-tile kernel instead
+  }
   wa.s = sa; wa.B = B; wa.n_tiles = n_tiles; wa.n_split = p->n_split;
   wa.trace = g_ws_trace;
   const int g = (int)(dense < grid ? (dense > 0 ? dense : 1) : grid);

@@ -28,7 +28,7 @@ for i in range(3):
         t = buf.cpu().numpy().reshape(6, 256, 2)
         t0 = t[5, 0, 1]
         print(f"layer {layer}: n_c={t[5,1,0]} n_f={t[5,1,1]}  prologue {(t0 - t[5,2,0]) / 1e3:.2f} us, CTA lifetime {(t[5,2,1] - t[5,2,0]) / 1e3:.2f} us (times in us after the prologue)")
-        names = ["dw0", "dw7", "mma", "ep0", "ep7"]
+        names = ["dw0", "xld", "mma", "ep0", "ep7"]
         ev = []
         for r in range(5):
             for tag, ts in t[r]:
