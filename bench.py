@@ -251,6 +251,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     lib = _native.lib()
@@ -399,6 +400,38 @@ def main():
     barrier()
     pad_ms = p0.elapsed_time(p1) / pad_steps
 
+    # ---- validation (outside every timed region): NCCL gathers results, nothing on the data path -----
+    # Every rank runs a small COMMON batch (same seed) and its own shard of a split batch; the per-utterance
+    # checksums (integer sums of the float bit patterns) and lengths are all_gathered to every rank, and rank 0
+    # checks that all GPUs produced identical bits and that the union of the shards equals the unsharded run.
+    validation = None
+    if world > 1:
+        from telugu_asr_b200.synth import draw_lengths as _dl, make_waveforms as _mw
+        vl = _dl(16 * world, 8000, 64000, seed=99)
+        vw, vl = _mw(vl, seed=99, dist="tilt")
+
+        def _run(idx):
+            nm = -(-int(vl[idx].max()) // 4) * 4
+            o, m, l3 = fe(torch.from_numpy(np.ascontiguousarray(vw[idx][:, :nm])).to(dev), torch.from_numpy(vl[idx]).to(dev),
+                          max_length=int(vl[idx].max()))
+            cs = torch.stack([o[j, : int(l3[j])].contiguous().view(torch.int32).to(torch.int64).sum() for j in range(len(idx))])
+            return cs, l3.to(torch.int64)
+
+        all_idx = np.arange(len(vl))
+        cs_all, l3_all = _run(all_idx)                                   # the whole batch on this GPU
+        mine = np.asarray(tasr.shard_by_length(vl, world)[rank])
+        cs_mine, l3_mine = _run(mine)                                    # this rank's shard
+        full = torch.zeros((len(vl), 2), dtype=torch.int64, device=dev)
+        full[torch.from_numpy(mine).to(dev), 0] = cs_mine
+        full[torch.from_numpy(mine).to(dev), 1] = l3_mine
+        dist.all_reduce(full, op=dist.ReduceOp.SUM)                      # union of the shards (disjoint rows)
+        gathered = [torch.zeros_like(cs_all) for _ in range(world)]
+        dist.all_gather(gathered, cs_all)                                # every GPU's result for the common batch
+        same_bits = all(bool(torch.equal(g_, cs_all)) for g_ in gathered)
+        union_ok = bool(torch.equal(full[:, 0], cs_all) and torch.equal(full[:, 1], l3_all))
+        validation = {"collective": "nccl all_gather / all_reduce of per-utterance checksums and lengths (validation only)",
+                      "utterances": int(len(vl)), "all_gpus_bit_identical": same_bits, "shard_union_equals_unsharded": union_ok}
+
     # ---- reduce over ranks: max time, sum of audio ------------------------------------------
     t = torch.tensor([ms_total, e2e_ms, audio_s, float(h2d), float(d2h), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -467,6 +500,7 @@ def main():
                     "f32_padded_single_stream": {"value": audio_s / (pad_ms * 1e-3), "ms_per_step": pad_ms,
                                                  "h2d_bytes_per_step": int(pb.h2d_bytes), "note": "rank 0; padded float32 [B,N_max] H2D, no overlap"}},
             "stages": stages,
+            "validation": validation,
             "gpu_launches": int(float(tsum[5])) if world > 1 else launches,
             "clocks": clocks,
         }
