@@ -489,7 +489,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
                          "kernel_share_of_step": k_ms / (ms_total / args.steps),
-                         "note": "HBM is the contract bound (SURVEY.md 8d); the kernel is issue-bound: ~530 warp instructions per frame of FFT/mel work, see profiles/ and DESIGN.md"},
+                         "note": "HBM is the contract bound (SURVEY.md 8d); the kernel is latency-bound at 16 resident warps/SM (61 % issue, 39 % FMA pipe, 18 % DRAM in ncu; an FP32x2 variant with 31 % fewer instructions takes the same time), see DESIGN.md 4.2; kernel_ms is its single-stream time, the step overlaps two batches"},
             "e2e": {"value": e2e_val, "unit": "audio-seconds/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps, "gpu_launches": e2e_launches,
                     "matches_device_resident_result": e2e_ok,
