@@ -600,3 +600,33 @@ def test_interleaved_streams_keep_batches_apart(cuda_device):
     torch.cuda.synchronize()
     for g, r in zip(got, refs):
         assert all(torch.equal(a, b) for a, b in zip(g, r))
+
+
+def test_long_utterance_and_odd_batches(cuda_device):
+    """Shapes away from the benchmark: a 5-minute utterance next to a 0.3 s one (29 998 frames, 235 conv tiles),
+    batch 1, and a batch where every utterance is shorter than the receptive field of the stack."""
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    fe = tasr.FrontEnd(math="tf32")
+    fe.set_weights(weights, cuda_device)
+    lens = [4_800_000, 4_800]
+    wav, ln = oracle.make_waveforms(lens, seed=51, dist="tilt")
+    out, mask, len3, feats, nf = fe(gpu(wav, cuda_device), gpu(ln, cuda_device), return_features=True)
+    torch.cuda.synchronize()
+    assert nf.tolist() == [29998, 28] and tuple(out.shape) == (2, 3743, 192)
+    ref_len = oracle.conv_lengths_ref(np.array([29998, 28], np.int32))
+    assert len3.tolist() == ref_len[-1].tolist() and mask.shape[1] == int(ref_len[-1].max())
+    # the first second of the long utterance against the oracle, with the whole utterance's peak gain
+    # (frames depend only on their own samples once the gain is fixed; the full 5 minutes take too long on the CPU)
+    g = np.float32(1.0) / (np.abs(wav[0]).max() + np.float32(1e-9))
+    p = oracle.FeatParams(**dict(tasr.REFERENCE_SPEECH_CONFIG, normalize_signal=False))
+    ref = oracle.featurizer_ref.featurize_ref((wav[0, :16_000] * g).astype(np.float32), p, dtype=np.float64)
+    assert np.abs(feats[0, : ref.shape[0], :, 0].cpu().numpy() - ref).max() <= LOGMEL_TOL
+    assert not feats[1, 28:].any()
+    # the short utterance: valid positions equal the run on its own (its third conv length is negative in the
+    # reference's float arithmetic, i.e. no valid position; the second layer has one)
+    o1, m1, l1 = fe(gpu(wav[1:2, :4800].copy(), cuda_device), gpu(ln[1:2], cuda_device))
+    assert int(l1[0]) == int(len3[1]) == int(ref_len[-1][1]) and o1.shape[1] == 0
+    # everything shorter than the receptive field: zero-length outputs, empty mask
+    o0, m0, l0 = fe(torch.zeros((3, 4000), device=cuda_device), torch.tensor([4000, 399, 0], dtype=torch.int32, device=cuda_device))
+    assert l0.tolist() == [int(x) for x in oracle.conv_lengths_ref(np.array([23, 0, 0], np.int32))[-1]]
+    assert o0.shape[0] == 3 and m0.shape[0] == 3
