@@ -630,3 +630,25 @@ def test_long_utterance_and_odd_batches(cuda_device):
     o0, m0, l0 = fe(torch.zeros((3, 4000), device=cuda_device), torch.tensor([4000, 399, 0], dtype=torch.int32, device=cuda_device))
     assert l0.tolist() == [int(x) for x in oracle.conv_lengths_ref(np.array([23, 0, 0], np.int32))[-1]]
     assert o0.shape[0] == 3 and m0.shape[0] == 3
+
+
+def test_logmel_config4_full_batch_on_one_gpu(feat, cuda_device):
+    """BASELINE.json configs[3] unsharded: 1024 x 30 s on one GPU (96 256 valid tiles, i.e. more than 256 per
+    persistent CTA, which exercises the kernel's multi-round tile lists).  Checked through batch invariance:
+    every utterance must equal, bit for bit, the same utterance featurised in a batch of 8."""
+    base, _ = oracle.make_waveforms([480000] * 8, seed=3, dist="tilt")
+    scale = (1.0 - 0.0005 * (np.arange(1024) % 11)).astype(np.float32)
+    w = torch.from_numpy(base).to(cuda_device).repeat(128, 1) * torch.from_numpy(scale).to(cuda_device)[:, None]
+    ln = torch.full((1024,), 480000, dtype=torch.int32, device=cuda_device)
+    ln[5], ln[1000] = 16000, 399
+    out, nf = feat(w, ln)
+    assert tuple(out.shape) == (1024, 2998, 80, 1)
+    ref_nf = torch.full((1024,), 2998, dtype=torch.int32, device=cuda_device)
+    ref_nf[5], ref_nf[1000] = 98, 0
+    assert torch.equal(nf, ref_nf)
+    for lo in (0, 496, 1016):
+        small, nfs = feat(w[lo: lo + 8].contiguous(), ln[lo: lo + 8].contiguous())
+        assert torch.equal(small, out[lo: lo + 8]) and torch.equal(nfs, nf[lo: lo + 8])
+    assert not out[5, 98:].any() and not out[1000].any()
+    ref = oracle.logmel_ref(w[3].cpu().numpy(), dtype=np.float64)
+    assert np.abs(out[3, :, :, 0].cpu().numpy() - ref).max() <= LOGMEL_TOL
