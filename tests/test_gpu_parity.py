@@ -652,3 +652,70 @@ def test_logmel_config4_full_batch_on_one_gpu(feat, cuda_device):
     assert not out[5, 98:].any() and not out[1000].any()
     ref = oracle.logmel_ref(w[3].cpu().numpy(), dtype=np.float64)
     assert np.abs(out[3, :, :, 0].cpu().numpy() - ref).max() <= LOGMEL_TOL
+
+
+def test_kernels_do_not_write_outside_their_outputs(cuda_device):
+    """Memory-safety check in lieu of compute-sanitizer (closed on this pool): every output buffer is carved out
+    of a canary-filled arena and the guard zones on both sides must come back untouched, on a ragged batch whose
+    shapes are not multiples of any tile size."""
+    G = 4096                                   # guard floats on either side (16 KB, keeps 16-byte alignment)
+    CANARY = 1234.5
+
+    def arena(n, dtype=torch.float32):
+        a = torch.full((n + 2 * G,), CANARY, dtype=dtype, device=cuda_device)
+        return a, a[G: G + n]
+
+    def intact(a, n):
+        return bool((a[:G] == CANARY).all() and (a[G + n:] == CANARY).all())
+
+    lib = _native.lib()
+    st = _native.stream_ptr()
+    lens = np.array([37777, 5281, 400, 399, 16001, 12345, 1, 0, 29999], dtype=np.int32)
+    wav, ln = oracle.make_waveforms(lens, seed=61, dist="tilt")
+    B, n_max = wav.shape
+    w, l = gpu(wav, cuda_device), gpu(ln, cuda_device)
+    feat = tasr.SpeechFeaturizer(**tasr.REFERENCE_SPEECH_CONFIG)
+    h = feat._handle(cuda_device)
+    T = feat.get_nframes(n_max)
+    # ingest
+    pb = tasr.PackedBatch(B, n_max, cuda_device, pcm16=True)
+    from telugu_asr_b200.synth import to_pcm16
+    pb.fill([to_pcm16(wav[b, :L]) for b, L in enumerate(lens)])
+    pb.to_device()
+    wa, wv = arena(B * pb.n_max)
+    _native.check(lib.tasr_unpack_pcm16(pb.dev_packed.data_ptr(), pb.dev_off.data_ptr(), pb.dev_len.data_ptr(), B, int(pb.max_len),
+                                        wv.data_ptr(), pb.n_max, st))
+    # peak, log-mel
+    pa, pv = arena(B)
+    _native.check(lib.tasr_absmax_f32(w.data_ptr(), l.data_ptr(), B, w.stride(0), pv.data_ptr(), st))
+    fa, fv = arena(B * T * 80)
+    na, nv = arena(B, torch.int32)
+    _native.check(lib.tasr_logmel_f32(h, w.data_ptr(), l.data_ptr(), pv.data_ptr(), B, w.stride(0), fv.data_ptr(), T, nv.data_ptr(), st))
+    # the three separable convs (ragged TF32 path and FP32 path)
+    sub = tasr.Conv1DSubsamplingLayer(192, tasr.REFERENCE_SUBSAMPLING_CONFIG, math="tf32")
+    sub.set_weights(oracle.glorot_subsampling_weights(192, 80, seed=7), cuda_device)
+    sub._ensure_plans()
+    x, t_in, ok = fv, T, []
+    for i, cout in enumerate(sub.filters):
+        t_out = (t_in - 9) // 2 + 1
+        ya, yv = arena(B * t_out * cout)
+        _native.check(lib.tasr_sepconv1d_tf32_ragged(sub._plans[i], x.data_ptr(), nv.data_ptr(), i, B, t_in, yv.data_ptr(), t_out, st))
+        ya2, yv2 = arena(B * t_out * cout)
+        ls = sub._layer_struct(i)
+        _native.check(lib.tasr_sepconv1d_f32(x.data_ptr(), B, t_in, ctypes.byref(ls), yv2.data_ptr(), t_out, st))
+        ok.append((ya, ya2, B * t_out * cout))
+        x, t_in = yv, t_out
+    # lengths + mask
+    la, lv = arena(3 * B, torch.int32)
+    ma, mv = arena(B * t_in)
+    k3 = (ctypes.c_int32 * 3)(9, 9, 9); s3 = (ctypes.c_int32 * 3)(2, 2, 2); z3 = (ctypes.c_int32 * 3)(0, 0, 0)
+    _native.check(lib.tasr_conv_lengths_mask(nv.data_ptr(), B, 3, k3, s3, z3, lv.data_ptr(), mv.data_ptr(), t_in, st))
+    torch.cuda.synchronize()
+    assert intact(wa, B * pb.n_max) and intact(pa, B) and intact(fa, B * T * 80)
+    assert bool((na[:G] == int(CANARY)).all() and (na[G + B:] == int(CANARY)).all())
+    for ya, ya2, n in ok:
+        assert intact(ya, n) and intact(ya2, n)
+    assert bool((la[:G] == int(CANARY)).all() and (la[G + 3 * B:] == int(CANARY)).all()) and intact(ma, B * t_in)
+    # and the values written inside are the ordinary results
+    ref, nref = feat(w, l)
+    assert torch.equal(fv.view(B, T, 80, 1), ref) and torch.equal(nv, nref)
