@@ -26,16 +26,15 @@
 //
 // Per-lane constants (half-window, transpose twiddles) live in registers for the whole
 // persistent loop.  Twiddles are float64-derived tables.
-#include "common.cuh"
+#include "logmel_common.cuh"
 #include <stdlib.h>
 
 using namespace tasr;
 
+using namespace tasr_lm;
+
 namespace {
 
-#include "mel_geometry.inc"
-
-constexpr int kTileFrames = 32;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kWavSmem = 5376;          // (32-1)*160+400 = 5360, +16 floats lanes 8..15 touch at m2=12
@@ -43,8 +42,6 @@ constexpr int kWavSlots = kWavSmem / 4 / kThreads + 1;   // float4 slots per thr
 constexpr int kScrStride = 17;          // float2 units; odd -> conflict-free transposed reads
 constexpr int kScrPerFrame = 16 * kScrStride;
 constexpr int kPStride = kBins + 4;     // 261, odd; columns 257..260 stay zero (band padding of the generic path)
-constexpr int kOutStride = kMel + 1;    // 81
-constexpr int kPadChunkRows = 128;      // rows of collate padding zero-filled per work item
 constexpr int kChunkUtt = 1024;         // utterances whose work items are indexed at a time (4 per thread)
 
 struct __align__(16) Smem {
@@ -61,14 +58,6 @@ struct __align__(16) Smem {
 };
 static_assert(sizeof(float) * kTileFrames * kOutStride <= sizeof(float2) * kWarps * 2 * kScrPerFrame,
               "output staging must fit in the transpose scratch");
-
-// Per-FFT-bin weights of the fixed-geometry mel projection, passed BY VALUE as a kernel parameter so
-// that they sit in the constant bank and FFMA reads them as operands (no load instruction):
-// wr[k] = W[k, seg(k)] (rising side of bin seg(k)), wf[k] = W[k, seg(k)-1] (falling side of the bin below).
-struct MelFixedW {
-  float wr[256];
-  float wf[256];
-};
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -108,71 +97,6 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
   for (int d = 0; d < 4; ++d) fft4(v[4 * d], v[4 * d + 1], v[4 * d + 2], v[4 * d + 3]);
 }
 #define X16(v, k) (v)[((k) >> 2) + 4 * ((k) & 3)]
-
-__device__ __forceinline__ void st_global_v4(float* p, float4 v) {
-  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-// log2 of a NORMAL positive float (the argument is clamped to output_floor >= FLT_MIN first, so the
-// denormal rescue sequence of __log2f is dead weight): one MUFU.
-__device__ __forceinline__ float lg2_normal(float x) {
-  float r;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-struct LogmelArgs {
-  const float* wav;
-  const int32_t* len;
-  const float* peak;       // may be null when !normalize
-  float* out;
-  int32_t* n_frames;
-  const float* hwin;
-  const float2* tw256;
-  const float2* tw512;
-  const float4* band_w;
-  const MelBands* bands;
-  int64_t row_stride;
-  int32_t B, T_max, tiles_per_row;
-  int32_t normalize;
-  int32_t pad_end;         // tf.signal.stft(pad_end=True): ceil(N/160) frames, the tail zero padded
-  int32_t mode;            // 0: mel projection + log; 1: log of the first 80 power bins ("spectrogram")
-  float preemph, floor_, log_scale;
-};
-
-__device__ __forceinline__ int frames_of(int n, const LogmelArgs& a) {   // src/speech_featurizer.py:163-166
-  const int Tb = a.pad_end ? (n > 0 ? (n + kFrameStep - 1) / kFrameStep : 0)
-                           : ((n >= kFrameLen) ? 1 + (n - kFrameLen) / kFrameStep : 0);
-  return min(Tb, a.T_max);
-}
-
-// ---- fixed-geometry mel projection (config/model.yaml filterbank), fully unrolled ------------------
-// Warp W owns mel bins [kMelGrp[W], kMelGrp[W+1]).  It walks segments m = first..last+1; in segment m
-// each power bin k is loaded once and accumulated into bin m (rising weight) and bin m-1 (falling
-// weight); bin m-1 is complete when segment m ends.  Summation is in ascending k, like a dot product.
-template <int M, int M0, int M1>
-struct MelSeg {
-  static __device__ __forceinline__ void run(const float* __restrict__ Prow, const MelFixedW& w, float* __restrict__ srow,
-                                             float floor_, float scale, float acc_prev) {
-    float acc_cur = 0.0f;
-    constexpr int kBegin = kMelSegStart[M], kEnd = kMelSegStart[M + 1];
-#pragma unroll
-    for (int k = kBegin; k < kEnd; ++k) {
-      const float p = Prow[k];
-      if (M < M1) acc_cur = fmaf(p, w.wr[k], acc_cur);
-      if (M > M0) acc_prev = fmaf(p, w.wf[k], acc_prev);
-    }
-    if (M > M0) srow[M - 1] = lg2_normal(fmaxf(acc_prev, floor_)) * scale;
-    if constexpr (M < M1) MelSeg<M + 1, M0, M1>::run(Prow, w, srow, floor_, scale, acc_cur);
-  }
-};
-
-template <int W>
-__device__ __forceinline__ void mel_fixed_group(const float* Prow, const MelFixedW& w, float* srow, float floor_, float scale) {
-  MelSeg<kMelGrp[W], kMelGrp[W], kMelGrp[W + 1]>::run(Prow, w, srow, floor_, scale, 0.0f);
-}
 
 template <bool FIXED>
 __global__ void __launch_bounds__(kThreads, 2)

@@ -1,0 +1,93 @@
+// Shared pieces of the log-mel kernel (logmel.cu; also used by the experiments under tools/experiments/):
+// argument block, frame count, the compiled-in mel filterbank structure
+// and its unrolled projection, small PTX helpers.
+#pragma once
+#include "common.cuh"
+
+namespace tasr_lm {
+
+using namespace tasr;
+
+#include "mel_geometry.inc"
+
+constexpr int kTileFrames = 32;
+constexpr int kOutStride = kMel + 1;    // 81
+constexpr int kPadChunkRows = 128;      // rows of collate padding zero-filled per work item
+
+
+// Per-FFT-bin weights of the fixed-geometry mel projection, passed BY VALUE as a kernel parameter so
+// that they sit in the constant bank and FFMA reads them as operands (no load instruction):
+// wr[k] = W[k, seg(k)] (rising side of bin seg(k)), wf[k] = W[k, seg(k)-1] (falling side of the bin below).
+struct MelFixedW {
+  float wr[256];
+  float wf[256];
+};
+
+__device__ __forceinline__ void st_global_v4(float* p, float4 v) {
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// log2 of a NORMAL positive float (the argument is clamped to output_floor >= FLT_MIN first, so the
+// denormal rescue sequence of __log2f is dead weight): one MUFU.
+__device__ __forceinline__ float lg2_normal(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+
+struct LogmelArgs {
+  const float* wav;
+  const int32_t* len;
+  const float* peak;       // may be null when !normalize
+  float* out;
+  int32_t* n_frames;
+  const float* hwin;
+  const float2* tw256;
+  const float2* tw512;
+  const float4* band_w;
+  const MelBands* bands;
+  int64_t row_stride;
+  int32_t B, T_max, tiles_per_row;
+  int32_t normalize;
+  int32_t pad_end;         // tf.signal.stft(pad_end=True): ceil(N/160) frames, the tail zero padded
+  int32_t mode;            // 0: mel projection + log; 1: log of the first 80 power bins ("spectrogram")
+  float preemph, floor_, log_scale;
+};
+
+__device__ __forceinline__ int frames_of(int n, const LogmelArgs& a) {   // src/speech_featurizer.py:163-166
+  const int Tb = a.pad_end ? (n > 0 ? (n + kFrameStep - 1) / kFrameStep : 0)
+                           : ((n >= kFrameLen) ? 1 + (n - kFrameLen) / kFrameStep : 0);
+  return min(Tb, a.T_max);
+}
+
+// ---- fixed-geometry mel projection (config/model.yaml filterbank), fully unrolled ------------------
+// Warp W owns mel bins [kMelGrp[W], kMelGrp[W+1]).  It walks segments m = first..last+1; in segment m
+// each power bin k is loaded once and accumulated into bin m (rising weight) and bin m-1 (falling
+// weight); bin m-1 is complete when segment m ends.  Summation is in ascending k, like a dot product.
+template <int M, int M0, int M1>
+struct MelSeg {
+  static __device__ __forceinline__ void run(const float* __restrict__ Prow, const MelFixedW& w, float* __restrict__ srow,
+                                             float floor_, float scale, float acc_prev) {
+    float acc_cur = 0.0f;
+    constexpr int kBegin = kMelSegStart[M], kEnd = kMelSegStart[M + 1];
+#pragma unroll
+    for (int k = kBegin; k < kEnd; ++k) {
+      const float p = Prow[k];
+      if (M < M1) acc_cur = fmaf(p, w.wr[k], acc_cur);
+      if (M > M0) acc_prev = fmaf(p, w.wf[k], acc_prev);
+    }
+    if (M > M0) srow[M - 1] = lg2_normal(fmaxf(acc_prev, floor_)) * scale;
+    if constexpr (M < M1) MelSeg<M + 1, M0, M1>::run(Prow, w, srow, floor_, scale, acc_cur);
+  }
+};
+
+template <int W>
+__device__ __forceinline__ void mel_fixed_group(const float* Prow, const MelFixedW& w, float* srow, float floor_, float scale) {
+  MelSeg<kMelGrp[W], kMelGrp[W], kMelGrp[W + 1]>::run(Prow, w, srow, floor_, scale, 0.0f);
+}
+
+
+}  // namespace tasr_lm
