@@ -454,11 +454,12 @@ def main():
         k_ms = stage_us.get("logmel_kernel", float("nan")) * 1e-3
         peak, peak_src = measured_peak()
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, ncu_lm, tj = None, None, {}
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
                 tj = json.load(fh)
-            traffic = next((v.get("dram_bytes_per_launch") for k, v in tj.items() if k.startswith("logmel_kernel") and isinstance(v, dict)), None)
+            ncu_lm = next((v for k, v in tj.items() if k.startswith("logmel_kernel") and isinstance(v, dict)), None)
+            traffic = ncu_lm.get("dram_bytes_per_launch") if ncu_lm else None
         except Exception:
             pass
         # per-stage algorithmic bytes: valid samples / valid rows only for the ragged stages
@@ -489,6 +490,8 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
                          "kernel_share_of_step": k_ms / (ms_total / args.steps),
+                         "ncu": ({"source": tj.get("source"), **{kk: ncu_lm.get(kk) for kk in ("dram_pct", "issue_active_pct", "fma_pipe_pct", "warp_instructions", "registers", "warps_active_pct")}}
+                                 if ncu_lm else None),
                          "note": "HBM is the contract bound (SURVEY.md 8d); the kernel is latency-bound at 16 resident warps/SM (61 % issue, 39 % FMA pipe, 18 % DRAM in ncu; an FP32x2 variant with 31 % fewer instructions takes the same time), see DESIGN.md 4.2; kernel_ms is its single-stream time, the step overlaps two batches"},
             "e2e": {"value": e2e_val, "unit": "audio-seconds/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps, "gpu_launches": e2e_launches,

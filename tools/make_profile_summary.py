@@ -72,7 +72,10 @@ for row in r[2:]:
         except ValueError:
             vals[label] = v
     full.append((k, vals))
-    traffic[k] = {"dram_bytes_per_launch": int((vals["dram rd MB"] + vals["dram wr MB"]) * 1e6), "ncu_time_us": vals["time us"]}
+    traffic[k] = {"dram_bytes_per_launch": int((vals["dram rd MB"] + vals["dram wr MB"]) * 1e6), "ncu_time_us": vals["time us"],
+                  "dram_pct": vals["DRAM %"], "issue_active_pct": vals["issue %"], "fma_pipe_pct": vals["FMA pipe %"],
+                  "tensor_pipe_pct": vals["tensor %"], "warp_instructions": int(vals["warp inst M"] * 1e6),
+                  "registers": int(vals["regs"]), "warps_active_pct": vals["warps act %"]}
 
 bench_line = open(os.path.join(G, f"bench_{tag}.log")).read().strip().splitlines()[-1]
 bj = json.loads(bench_line)
