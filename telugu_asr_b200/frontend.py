@@ -102,6 +102,8 @@ class CapturedFrontEnd:
             with torch.cuda.graph(self.graph):
                 self.encoder_input, self.padding_mask, self.len3 = self.fe(self.wav, self.lengths, max_length=self.max_length)
             self.kernels_per_replay = int(_native.lib().tasr_launch_count() - l0)
+        # the graph holds raw pointers to the plans' packed weights: a later set_weights() would free them
+        self._plans_at_capture = tuple(self.fe.subsampling._plans or ())
 
     def load(self, wav: torch.Tensor, lengths: torch.Tensor) -> None:
         """Copy a [batch, <= n_max] device batch into the static input buffers (stream ordered)."""
@@ -109,6 +111,9 @@ class CapturedFrontEnd:
         self.lengths.copy_(lengths.to(torch.int32), non_blocking=True)
 
     def replay(self):
+        if tuple(self.fe.subsampling._plans or ()) != self._plans_at_capture:
+            raise RuntimeError("CapturedFrontEnd: the subsampling weights changed after capture (set_weights destroys the "
+                               "plans the graph points to); capture a new CapturedFrontEnd")
         self.graph.replay()
         return self.encoder_input, self.padding_mask, self.len3
 

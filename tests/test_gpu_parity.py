@@ -719,3 +719,14 @@ def test_kernels_do_not_write_outside_their_outputs(cuda_device):
     # and the values written inside are the ordinary results
     ref, nref = feat(w, l)
     assert torch.equal(fv.view(B, T, 80, 1), ref) and torch.equal(nv, nref)
+
+
+def test_captured_graph_refuses_stale_plans(cuda_device):
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    fe = tasr.FrontEnd(math="tf32")
+    fe.set_weights(weights, cuda_device)
+    cap = tasr.CapturedFrontEnd(fe, 2, 16000, cuda_device)
+    cap.replay()
+    fe.set_weights(oracle.glorot_subsampling_weights(192, 80, seed=8), cuda_device)
+    with pytest.raises(RuntimeError, match="weights changed after capture"):
+        cap.replay()
