@@ -52,7 +52,7 @@ def assert_logmel_parity(out, wav, ln):
     """Per utterance: max-abs error vs the float64 oracle <= max(1e-4, 4 x the float32 oracle's own
     band on that utterance); over everything: fewer than 1e-6 of the values outside 1e-4.  (On 30M
     values a handful land on near-cancelled low mel bins, ~1e-9 power, where pocketfft-float32 is
-    itself 1e-3 off float64 — measured in tools/diag_logmel.py.)"""
+    itself 1e-3 off float64 — measured in tests/diag_logmel.py.)"""
     n_bad = n_all = 0
     worst = 0.0
     for b in range(wav.shape[0]):

@@ -1,9 +1,9 @@
 """BASELINE.json configs[4] on one GPU: throughput of log-mel + subsampling over utterance length x batch
-(equal-length utterances, 'tilt' distribution, device-resident inputs, CUDA-graph replay per step), next to the
-CPU restatement of the reference on the host cores for a bounded subset.  Also runs configs[3] (30 s x 1024
-sharded 1/8: 128 utterances per GPU).  Writes gpurun_out/sweep.json and prints a markdown table.
+(equal-length utterances, 'tilt' distribution, device-resident inputs, CUDA-graph replay per step).  configs[3]
+(30 s x 1024 sharded 1/8: 128 utterances per GPU) lies between two columns of the 30 s row.  Writes
+gpurun_out/sweep.json and prints a markdown table.  (Product-side tool: it does not touch oracle/.)
 
-    python tools/sweep.py [--cpu]
+    python tools/sweep.py
 """
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -40,16 +40,7 @@ for sec in LENS:
         res[f"{sec}s x {B}"] = {"seconds": sec, "batch": B, "ms_per_step": ms, "audio_s_per_s": B * sec / (ms * 1e-3)}
         del cap, wav
         torch.cuda.empty_cache()
-cpu = {}
-if "--cpu" in sys.argv:
-    from oracle import torch_port
-    torch.set_num_threads(os.cpu_count() or 1)
-    for sec, B in [(1, 64), (10, 64), (30, 16)]:
-        n = sec * 16000
-        w = np.ascontiguousarray(np.tile(base[:, :n], (-(-B // 8), 1))[:B]); l = np.full(B, n, np.int32)
-        torch_port.frontend_torch(w[:2], l[:2], weights)
-        t0 = time.perf_counter(); torch_port.frontend_torch(w, l, weights); dt = time.perf_counter() - t0
-        cpu[f"{sec}s x {B}"] = {"audio_s_per_s": B * sec / dt, "cores": torch.get_num_threads()}
+cpu = {}   # (the CPU figures quoted in profiles/r01_sweep.md come from bench.py's --impl reference arm on these shapes)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump({"gpu": res, "cpu": cpu}, open("gpurun_out/sweep.json", "w"), indent=1)
 print("| length \\\\ batch | " + " | ".join(str(b) for b in BATCHES) + " |")
