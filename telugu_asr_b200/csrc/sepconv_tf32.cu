@@ -93,23 +93,31 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
   // writes the constant row for those frames.
   const bool run_needed = (r0 < cf);
 
+  // B (pw^T) chunks are fetched one chunk AHEAD of their use: chunks 0 and 1 up front, chunk kc+1 in the shadow
+  // of chunk kc's input loads (its stage is free once the MMAs of chunk kc-1 completed), so that thread 0 — and
+  // with it the whole CTA at the next barrier — does not sit waiting for the copy it has only just issued.
+  auto fetch_b = [&](int kc) {
+    const int sb = kc & 1;
+    mbar_expect_tx(bar_u + 8 * sb, bBytes);
+    bulk_g2s(sB_u + sb * bBytes, bsrc + (size_t)kc * NT * kKC, bBytes, bar_u + 8 * sb);
+  };
+  if (tid == 0) {
+    fetch_b(0);
+    if (a.n_chunks > 1) fetch_b(1);
+  }
   for (int kc = 0; kc < a.n_chunks; ++kc) {
     const int s = kc & 1, use = kc >> 1;
     if (kc >= 2) {                       // stage s is free once the MMAs of chunk kc-2 completed
       mbar_wait(bar_u + 8 * (2 + s), (use - 1) & 1);
       tc_fence_after();
     }
-    if (tid == 0) {
-      mbar_expect_tx(bar_u + 8 * s, bBytes);
-      bulk_g2s(sB_u + s * bBytes, bsrc + (size_t)kc * NT * kKC, bBytes, bar_u + 8 * s);
-    }
     // ---- depthwise for channels [c0, c0+32) -> A[s] ----------------------------------------
     const int c0 = kc * kKC;
     const int kvalid = min(kKC, C_in - c0);
     const bool cok = lane < kvalid;
-    if (run_needed) {
     float v[kWin];
     float w[9];
+    if (run_needed) {
     if (run_inside && kvalid == kKC) {   // common case: unpredicated loads at immediate offsets
       const float* xp = xrow + c0;
 #pragma unroll
@@ -123,6 +131,12 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
 #pragma unroll
       for (int k = 0; k < 9; ++k) w[k] = cok ? __ldg(a.dw + k * C_in + c0 + lane) : 0.0f;
     }
+    }
+    if (tid == 0 && kc >= 1 && kc + 1 < a.n_chunks) {   // (the loads above are in flight while this waits)
+      mbar_wait(bar_u + 8 * (2 + (s ^ 1)), ((kc - 1) >> 1) & 1);   // MMAs of chunk kc-1 done: its B stage is free
+      fetch_b(kc + 1);
+    }
+    if (run_needed) {
     unsigned char* As = sA + s * kABytes;
 #pragma unroll
     for (int j = 0; j < kRun; ++j) {
