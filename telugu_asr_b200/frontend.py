@@ -34,7 +34,13 @@ def load_reference_yaml(path: str):
     with open(path) as fh:
         cfg = yaml.safe_load(fh)
     mc = cfg.get("model_config", {})
-    return dict(cfg["speech_config"]), dict(mc.get("subsampling_config", {})), int(mc.get("d_model", REFERENCE_D_MODEL))
+    speech = dict(cfg["speech_config"])
+    # The reference loads its YAML through hydra/OmegaConf, whose resolver reads `1e-9` (no decimal point) as a
+    # float; plain PyYAML (YAML 1.1) leaves it a string.  Same result here.
+    for k in ("output_floor", "preemphasis", "lower_edge_hertz", "upper_edge_hertz", "padding"):
+        if isinstance(speech.get(k), str):
+            speech[k] = float(speech[k])
+    return speech, dict(mc.get("subsampling_config", {})), int(mc.get("d_model", REFERENCE_D_MODEL))
 
 
 class FrontEnd:

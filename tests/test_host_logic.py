@@ -159,3 +159,26 @@ def test_packed_batch_offsets_are_aligned_and_disjoint():
     assert used - sum(lens) < 8 * len(lens)
     o0, u0 = tasr.PackedBatch.offsets_for([])
     assert len(o0) == 0 and u0 == 0
+
+
+def test_builtin_reference_config_equals_the_reference_yaml():
+    """When the reference checkout is present (this container; not the GPU box), the constants this package ships
+    as REFERENCE_SPEECH_CONFIG / REFERENCE_SUBSAMPLING_CONFIG / d_model must be the reference's own
+    config/model.yaml values, key for key (config/conformer.yaml carries the same speech_config)."""
+    path = "/root/reference/config/model.yaml"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    sc, sub, d = tasr.load_reference_yaml(path)
+    for k, v in tasr.REFERENCE_SPEECH_CONFIG.items():
+        assert k in sc, k
+        assert (str(sc[k]) == str(v)) or (sc[k] == v), (k, sc[k], v)
+    assert set(sc) - set(tasr.REFERENCE_SPEECH_CONFIG) <= {"augmentation_config"}
+    assert d == tasr.frontend.REFERENCE_D_MODEL == 192
+    for k in ("kernel_size", "strides", "padding"):
+        assert list(sub[k]) == list(tasr.REFERENCE_SUBSAMPLING_CONFIG[k]), k
+    assert "activations" not in sub and "activation" in sub      # the key quirk the layer mirrors (encoder.py:25)
+    f = tasr.SpeechFeaturizer(**sc)
+    assert (f.frame_length, f.frame_step, f.fft_length, f.num_feature_bins) == (400, 160, 512, 80)
+    assert isinstance(sc["output_floor"], float) and sc["output_floor"] == 1e-9   # `1e-9` in the YAML: OmegaConf reads a float
+    sc2, _, _ = tasr.load_reference_yaml("/root/reference/config/conformer.yaml")
+    assert sc2 == sc
