@@ -5,7 +5,6 @@ padded_batch (src/dataset.py:171-175, 236-252), the mask derivation (model.py:80
 Conv1DSubsamplingLayer.call (encoder.py:50-71) — with every stage on the device."""
 from __future__ import annotations
 
-import os
 
 import torch
 import yaml

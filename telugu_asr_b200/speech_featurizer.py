@@ -18,7 +18,6 @@ from __future__ import annotations
 import ctypes as C
 from dataclasses import asdict, dataclass
 
-import numpy as np
 import torch
 
 from . import _native, tables
