@@ -135,6 +135,15 @@ int tasr_logmel_f32(const TasrFeaturizer* f, const float* wav, const int32_t* le
                     const float* peak_or_null, int32_t batch, int64_t row_stride, float* out,
                     int32_t t_max, int32_t* n_frames, tasr_stream_t stream);
 
+/* Lean variant for a feature tensor that is only an INTERMEDIATE (its one reader is the ragged separable
+ * convolution below, which never looks further than tasr_sepconv_ragged_margin() rows past the data): of the
+ * collate padding only rows n_frames[b] <= t < n_frames[b] + pad_fill_rows are written as 0.0; the rest of
+ * out[b] is left untouched.  Rows t < n_frames[b] and n_frames are identical to tasr_logmel_f32.  mfcc and
+ * per-frame normalisation handles are TASR_ERR_UNSUPPORTED (they post-process the whole tensor). */
+int tasr_logmel_f32_lean(const TasrFeaturizer* f, const float* wav, const int32_t* len,
+                         const float* peak_or_null, int32_t batch, int64_t row_stride, float* out,
+                         int32_t t_max, int32_t* n_frames, int32_t pad_fill_rows, tasr_stream_t stream);
+
 /* Replaces one tf.keras.layers.SeparableConv1D forward (encoder.py:31-40, called at :60):
  * y[b,t,o] = act( sum_c ( sum_k x[b, stride*t+k, c] * dw[k,c] ) * pw[c,o] + bias[o] ),
  * "valid" padding, t < t_out where t_out <= (t_in-kernel)/stride+1.  x [batch,t_in,c_in],
@@ -164,6 +173,17 @@ int tasr_sepconv_plan_set_pad_row(TasrSepConvPlan* plan, const float* pad_row_in
 const float* tasr_sepconv_plan_pad_row(const TasrSepConvPlan* plan);
 int tasr_sepconv1d_tf32_ragged(const TasrSepConvPlan* plan, const float* x, const int32_t* len0, int32_t shift,
                                int32_t batch, int32_t t_in, float* y, int32_t t_out, tasr_stream_t stream);
+
+/* Lean variant for an INTERMEDIATE activation tensor whose only reader is the next ragged layer of the stack
+ * (src/models/moonshine/encoder.py:58-68 keeps no intermediate): of the rows that only repeat the constant padding
+ * row — t >= ceil(len0[b] / 2^(shift+1)) — at least the first fill_rows are written (whole 128-row tiles), the
+ * tiles beyond are left untouched.  All other rows are identical to tasr_sepconv1d_tf32_ragged.
+ * tasr_sepconv_ragged_margin() is the number of input rows past ceil(len0[b] / 2^shift) that the ragged kernels
+ * may read: a producer in lean mode must be given fill_rows / pad_fill_rows >= that. */
+int32_t tasr_sepconv_ragged_margin(void);
+int tasr_sepconv1d_tf32_ragged_lean(const TasrSepConvPlan* plan, const float* x, const int32_t* len0, int32_t shift,
+                                    int32_t batch, int32_t t_in, float* y, int32_t t_out, int32_t fill_rows,
+                                    tasr_stream_t stream);
 
 /* Replaces math_util.get_conv_length applied per layer (src/utils/math_util.py:20-32,
  * encoder.py:60-68) and lengths_to_padding_mask (encoder.py:43-48).

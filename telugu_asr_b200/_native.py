@@ -50,6 +50,7 @@ _SIGNATURES = {
     "tasr_waveform_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "tasr_absmax_f32": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "tasr_logmel_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _vp, _vp]),
+    "tasr_logmel_f32_lean": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _vp, _i32, _vp]),
     "tasr_sepconv1d_f32": (C.c_int, [_vp, _i32, _i32, C.POINTER(TasrSepConvLayer), _vp, _i32, _vp]),
     "tasr_sepconv_plan_create": (C.c_int, [C.POINTER(TasrSepConvLayer), C.POINTER(_vp), _vp]),
     "tasr_sepconv_plan_destroy": (C.c_int, [_vp]),
@@ -57,6 +58,8 @@ _SIGNATURES = {
     "tasr_sepconv_plan_set_pad_row": (C.c_int, [_vp, _vp, _vp]),
     "tasr_sepconv_plan_pad_row": (C.c_void_p, [_vp]),
     "tasr_sepconv1d_tf32_ragged": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "tasr_sepconv_ragged_margin": (C.c_int32, []),
+    "tasr_sepconv1d_tf32_ragged_lean": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp]),
     "tasr_conv_lengths_mask": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32),
                                          C.POINTER(_i32), _vp, _vp, _i32, _vp]),
     "tasr_specaugment_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp]),
@@ -128,6 +131,20 @@ def require_cuda(t, name: str):
         raise RuntimeError(
             f"telugu_asr_b200: `{name}` must be a CUDA tensor — this package runs only on B200 "
             "(sm_100a) through libtasr_b200.so and has no CPU path")
+    return t
+
+
+poison_allocations = False
+
+
+def empty(shape, dtype, device):
+    """Output / intermediate allocation of the operators.  With `_native.poison_allocations = True` the buffer is
+    filled with NaN (floats) or a large negative value (ints) first, so that a test can prove no kernel consumes a
+    row that lean mode leaves unwritten."""
+    import torch
+    t = torch.empty(shape, dtype=dtype, device=device)
+    if poison_allocations and t.numel():
+        t.fill_(float("nan") if t.dtype.is_floating_point else -(2 ** 30))
     return t
 
 

@@ -147,8 +147,9 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
       const int u = 4 * tid + i;
       vt[i] = pt[i] = 0;
       if (u < nu) {
-        vt[i] = (frames_of(a.len[cb + u], a) + kTileFrames - 1) / kTileFrames;
-        const int pad_rows = a.T_max - vt[i] * kTileFrames;
+        const int Tu = frames_of(a.len[cb + u], a);
+        vt[i] = (Tu + kTileFrames - 1) / kTileFrames;
+        const int pad_rows = pad_limit(Tu, a) - vt[i] * kTileFrames;
         pt[i] = pad_rows > 0 ? (pad_rows + kPadChunkRows - 1) / kPadChunkRows : 0;
       }
       vs += vt[i]; ps += pt[i];
@@ -187,7 +188,7 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
     const int u = find(S.pcum, jp - poff);
     const int vt = S.vcum[u + 1] - S.vcum[u];
     const int r0 = vt * kTileFrames + (jp - poff - S.pcum[u]) * kPadChunkRows;
-    const int rows = min(kPadChunkRows, a.T_max - r0);
+    const int rows = min(kPadChunkRows, pad_limit(frames_of(a.len[cb + u], a), a) - r0);
     float* dst = a.out + ((size_t)(cb + u) * a.T_max + r0) * kMel;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = tid; i < rows * (kMel / 4); i += kThreads) st_global_v4(dst + 4 * i, z);
@@ -395,9 +396,9 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
 
 }  // namespace
 
-extern "C" int tasr_logmel_f32(const TasrFeaturizer* f, const float* wav, const int32_t* len,
-                               const float* peak, int32_t B, int64_t row_stride, float* out,
-                               int32_t T_max, int32_t* n_frames, tasr_stream_t stream) {
+static int logmel_launch(const TasrFeaturizer* f, const float* wav, const int32_t* len,
+                         const float* peak, int32_t B, int64_t row_stride, float* out,
+                         int32_t T_max, int32_t* n_frames, int32_t pad_fill_rows, tasr_stream_t stream) {
   if (!f || !wav || !len || !out || !n_frames) return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32: null argument");
   if (B < 0 || T_max < 0 || row_stride < 0) return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32: negative size");
   if (f->p.normalize_signal && !peak)
@@ -429,6 +430,7 @@ extern "C" int tasr_logmel_f32(const TasrFeaturizer* f, const float* wav, const 
   a.normalize = f->p.normalize_signal ? 1 : 0;
   a.pad_end = f->p.pad_end ? 1 : 0;
   a.mode = (f->p.feature_type == TASR_FEAT_SPECTROGRAM) ? 1 : 0;
+  a.pad_fill_rows = pad_fill_rows;
   a.preemph = f->p.preemphasis; a.floor_ = f->p.output_floor; a.log_scale = f->log_scale;
   // Persistent grid: two CTAs per SM; never more CTAs than work items (valid tiles + padding chunks <= total + B).
   const long long cap = total + B;
@@ -446,6 +448,21 @@ extern "C" int tasr_logmel_f32(const TasrFeaturizer* f, const float* wav, const 
   if (f->p.feature_type == TASR_FEAT_MFCC || f->p.normalize_zscore || f->p.normalize_min_max)
     return tasr_feature_post_launch(f, out, n_frames, B, T_max, st);
   return TASR_OK;
+}
+
+extern "C" int tasr_logmel_f32(const TasrFeaturizer* f, const float* wav, const int32_t* len,
+                               const float* peak, int32_t B, int64_t row_stride, float* out,
+                               int32_t T_max, int32_t* n_frames, tasr_stream_t stream) {
+  return logmel_launch(f, wav, len, peak, B, row_stride, out, T_max, n_frames, -1, stream);
+}
+
+extern "C" int tasr_logmel_f32_lean(const TasrFeaturizer* f, const float* wav, const int32_t* len,
+                                    const float* peak, int32_t B, int64_t row_stride, float* out,
+                                    int32_t T_max, int32_t* n_frames, int32_t pad_fill_rows, tasr_stream_t stream) {
+  if (pad_fill_rows < 0) return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32_lean: pad_fill_rows must be >= 0 (use tasr_logmel_f32 to write every row)");
+  if (f && (f->p.feature_type == TASR_FEAT_MFCC || f->p.normalize_zscore || f->p.normalize_min_max))
+    return fail(TASR_ERR_UNSUPPORTED, "tasr_logmel_f32_lean: mfcc / per-frame normalisation post-process the whole tensor; use tasr_logmel_f32");
+  return logmel_launch(f, wav, len, peak, B, row_stride, out, T_max, n_frames, pad_fill_rows, stream);
 }
 
 // Host side of the fixed-geometry check (called by tasr_featurizer_create): fills wr/wf from the dense

@@ -54,6 +54,8 @@ struct LogmelArgs {
   int32_t normalize;
   int32_t pad_end;         // tf.signal.stft(pad_end=True): ceil(N/160) frames, the tail zero padded
   int32_t mode;            // 0: mel projection + log; 1: log of the first 80 power bins ("spectrogram")
+  int32_t pad_fill_rows;   // < 0: every collate padding row (t >= n_frames[b]) is written as 0.0; >= 0: only the first
+                           // pad_fill_rows of them are guaranteed (lean mode: the rest of out[b] is left untouched)
   float preemph, floor_, log_scale;
 };
 
@@ -61,6 +63,11 @@ __device__ __forceinline__ int frames_of(int n, const LogmelArgs& a) {   // src/
   const int Tb = a.pad_end ? (n > 0 ? (n + kFrameStep - 1) / kFrameStep : 0)
                            : ((n >= kFrameLen) ? 1 + (n - kFrameLen) / kFrameStep : 0);
   return min(Tb, a.T_max);
+}
+
+// First row of out[b] that need not be written: T_max, or (lean mode) pad_fill_rows past the utterance's frames.
+__device__ __forceinline__ int pad_limit(int Tu, const LogmelArgs& a) {
+  return a.pad_fill_rows < 0 ? a.T_max : min(a.T_max, Tu + a.pad_fill_rows);
 }
 
 // ---- fixed-geometry mel projection (config/model.yaml filterbank), fully unrolled ------------------

@@ -162,6 +162,10 @@ struct SepArgs {
   const int32_t* len0;
   const float* pad_out;
   int32_t shift;
+  // lean mode (fill_rows >= 0): only the first fill_rows padding rows of y[b] — rows ceil(len0[b] / 2^(shift+1)) + i,
+  // i < fill_rows, rounded up to whole tiles — are guaranteed to be written; tiles beyond are left untouched
+  // (for an intermediate tensor whose only reader is the next ragged layer).  < 0: every row is written.
+  int32_t fill_rows;
 };
 
 }  // namespace tasr_sep

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
   if (a.len0 != nullptr) {               // CTA-uniform: leaves before any barrier / TMEM allocation
     cf = (max(a.len0[b], 0) + (1 << a.shift) - 1) >> a.shift;
     if (2 * t0 >= cf) {
+      if (a.fill_rows >= 0 && t0 >= ((cf + 1) >> 1) + a.fill_rows) return;   // lean: nobody reads this tile
       const int rows = min(kMT, a.T_out - t0), q4 = NT >> 2;   // q4 <= 64 float4 per row: one warp per row
       float* dst = a.y + ((size_t)b * a.T_out + t0) * a.C_out + n0;
       const float4* pr = reinterpret_cast<const float4*>(a.pad_out + n0);
@@ -313,7 +314,7 @@ extern "C" int tasr_sepconv_plan_destroy(TasrSepConvPlan* p) {
 }
 
 static int launch_tf32(const char* who, const TasrSepConvPlan* p, const float* x, const int32_t* len0, int32_t shift,
-                       int32_t B, int32_t T_in, float* y, int32_t T_out, tasr_stream_t stream) {
+                       int32_t B, int32_t T_in, float* y, int32_t T_out, tasr_stream_t stream, int32_t fill_rows = -1) {
   if (!p) return fail(TASR_ERR_BAD_ARG, "%s: null plan", who);
   int rc = validate_sepconv(who, x, B, T_in, &p->L, y, T_out);
   if (rc != TASR_OK) return rc;
@@ -325,8 +326,8 @@ static int launch_tf32(const char* who, const TasrSepConvPlan* p, const float* x
   a.x = x; a.dw = p->L.dw; a.bpack = p->d_bpack; a.bias = p->L.bias; a.y = y;
   a.T_in = T_in; a.T_out = T_out; a.C_in = p->L.c_in; a.C_out = p->L.c_out; a.NT = p->NT;
   a.n_chunks = p->n_chunks; a.act = p->L.activation;
-  a.len0 = len0; a.pad_out = p->d_pad_out; a.shift = shift;
-  if (p->use_ws) {
+  a.len0 = len0; a.pad_out = p->d_pad_out; a.shift = shift; a.fill_rows = fill_rows;
+  if (p->use_ws) {                       // (the persistent kernel always writes every row: fill_rows is a permission)
     const int wrc = tasr_sepconv_ws_launch(p, a, B, (cudaStream_t)stream);
     if (wrc >= 0) return wrc;            // launched (TASR_OK) or failed with an error code
   }
@@ -368,4 +369,17 @@ extern "C" int tasr_sepconv1d_tf32_ragged(const TasrSepConvPlan* p, const float*
   if (!p->pad_ready)
     return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32_ragged: call tasr_sepconv_plan_set_pad_row first (the input's padding row is unknown)");
   return launch_tf32("tasr_sepconv1d_tf32_ragged", p, x, len0, shift, B, T_in, y, T_out, stream);
+}
+
+extern "C" int32_t tasr_sepconv_ragged_margin(void) { return kWin; }
+
+extern "C" int tasr_sepconv1d_tf32_ragged_lean(const TasrSepConvPlan* p, const float* x, const int32_t* len0, int32_t shift,
+                                               int32_t B, int32_t T_in, float* y, int32_t T_out, int32_t fill_rows,
+                                               tasr_stream_t stream) {
+  if (!p || !len0) return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32_ragged_lean: null argument");
+  if (shift < 0 || shift > 29) return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32_ragged_lean: shift must be in [0,29]");
+  if (fill_rows < 0) return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32_ragged_lean: fill_rows must be >= 0 (use tasr_sepconv1d_tf32_ragged to write every row)");
+  if (!p->pad_ready)
+    return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32_ragged_lean: call tasr_sepconv_plan_set_pad_row first (the input's padding row is unknown)");
+  return launch_tf32("tasr_sepconv1d_tf32_ragged_lean", p, x, len0, shift, B, T_in, y, T_out, stream, fill_rows);
 }

@@ -44,12 +44,17 @@ def load_reference_yaml(path: str):
 
 class FrontEnd:
     def __init__(self, speech_config: dict | None = None, subsampling_config: dict | None = None,
-                 model_dim: int = REFERENCE_D_MODEL, math: str = "tf32", device=None, seed: int = 0):
+                 model_dim: int = REFERENCE_D_MODEL, math: str = "tf32", device=None, seed: int = 0,
+                 lean_intermediates: bool = True):
         self.featurizer = SpeechFeaturizer(**(speech_config or REFERENCE_SPEECH_CONFIG))
         self.subsampling = Conv1DSubsamplingLayer(
             model_dim=model_dim, subsampling_config=subsampling_config or REFERENCE_SUBSAMPLING_CONFIG,
             input_dim=self.featurizer.num_feature_bins, math=math, seed=seed, name="asr_encoder_conv_subsampling")
         self.device = torch.device(device) if device is not None else None
+        # The features and the first two layers' activations are intermediates of this object: far inside the
+        # collate padding nobody reads them (the ragged layers treat those rows as one constant row), so they are
+        # not written there.  Outputs are bit-identical; `return_features=True` always gets the full 0.0 padding.
+        self.lean_intermediates = bool(lean_intermediates)
 
     def set_weights(self, weights, device=None):
         self.subsampling.set_weights(weights, device or self.device)
@@ -65,9 +70,13 @@ class FrontEnd:
         t_max = None
         if max_length is not None:
             t_max = max(0, int(self.featurizer.get_nframes(int(max_length))))
-        feats, n_frames = self.featurizer.featurize_batch(wav, lengths, t_max=t_max)
-        out, mask, len_all = self.subsampling(feats, mask=n_frames, return_lengths=True,
-                                              max_frames=t_max if max_length is not None else None)
+        sub = self.subsampling
+        lean = (self.lean_intermediates and sub.math == "tf32" and sub.assume_zero_padding
+                and all(p == "valid" for p in sub.padding))
+        feats, n_frames = self.featurizer.featurize_batch(
+            wav, lengths, t_max=t_max, pad_fill_rows=sub.ragged_margin() if (lean and not return_features) else None)
+        out, mask, len_all = sub(feats, mask=n_frames, return_lengths=True,
+                                 max_frames=t_max if max_length is not None else None, lean_intermediates=lean)
         len3 = len_all[-1]
         if return_features:
             return out, mask, len3, feats, n_frames

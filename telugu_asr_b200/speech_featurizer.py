@@ -214,10 +214,12 @@ class SpeechFeaturizer:
 
     # ------------------------------------------------------------------ batched device path
     def featurize_batch(self, wav: torch.Tensor, lengths: torch.Tensor | None, out: torch.Tensor | None = None,
-                        t_max: int | None = None):
+                        t_max: int | None = None, pad_fill_rows: int | None = None):
         """wav [B, N_max] float32 CUDA (rows zero padded; padding is never read), lengths [B] int32
         CUDA -> (features [B, T_max, F, 1] with rows >= n_frames[b] equal to 0.0, n_frames [B] int32).
-        T_max defaults to get_nframes(N_max) clamped at 0, i.e. the collate's batch maximum."""
+        T_max defaults to get_nframes(N_max) clamped at 0, i.e. the collate's batch maximum.
+        `pad_fill_rows` (lean mode, for a feature tensor that only feeds the ragged subsampling): write just that
+        many 0.0 rows past each utterance's frames and leave the rest of the collate padding untouched."""
         _native.require_cuda(wav, "wav")
         dev = wav.device
         B, n_max = wav.shape
@@ -244,7 +246,7 @@ class SpeechFeaturizer:
             t_max = max(0, self.get_nframes(n_max)) if n_max >= 0 else 0
         F = self.num_feature_bins
         if out is None:
-            out = torch.empty((B, t_max, F, 1), dtype=torch.float32, device=dev)
+            out = _native.empty((B, t_max, F, 1), torch.float32, dev)
         else:
             if tuple(out.shape) != (B, t_max, F, 1) or not out.is_contiguous() or out.dtype != torch.float32:
                 raise ValueError(f"out must be a contiguous float32 [B={B}, T_max={t_max}, {F}, 1] tensor")
@@ -268,8 +270,14 @@ class SpeechFeaturizer:
             if ev is not None:   # bench.py: CUDA events around the dominant kernel, on its own stream
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            _native.check(L.tasr_logmel_f32(h, wav.data_ptr(), lengths.data_ptr(), peak_ptr, B, row_stride,
-                                            out.data_ptr(), t_max, n_frames.data_ptr(), st))
+            lean = (pad_fill_rows is not None and not self._normalize_zscore and not self._normalize_min_max
+                    and self.feature_type in (FeaturizerConfig.log_mel_spectrogram, FeaturizerConfig.spectrogram))
+            if lean:
+                _native.check(L.tasr_logmel_f32_lean(h, wav.data_ptr(), lengths.data_ptr(), peak_ptr, B, row_stride,
+                                                     out.data_ptr(), t_max, n_frames.data_ptr(), int(pad_fill_rows), st))
+            else:
+                _native.check(L.tasr_logmel_f32(h, wav.data_ptr(), lengths.data_ptr(), peak_ptr, B, row_stride,
+                                                out.data_ptr(), t_max, n_frames.data_ptr(), st))
             if ev is not None:
                 e1.record()
                 ev.append((e0, e1))

@@ -222,8 +222,17 @@ class Conv1DSubsamplingLayer:
                 _native.check(L.tasr_conv_lengths_mask(lengths.data_ptr(), B, n, k, s, same, len_out.data_ptr(), None, 0, st))
         return len_out, mask
 
+    @staticmethod
+    def ragged_margin() -> int:
+        """Rows past an utterance's data that the ragged kernels may read from their input (see
+        tasr_sepconv_ragged_margin): what a lean producer has to keep filled."""
+        return int(_native.lib().tasr_sepconv_ragged_margin())
+
     def __call__(self, inputs: torch.Tensor, training: bool = False, mask=None, return_lengths: bool = False,
-                 max_frames: int | None = None):
+                 max_frames: int | None = None, lean_intermediates: bool = False):
+        """`lean_intermediates` (ragged TF32 path only): the outputs of all layers but the last are not
+        materialised far inside the padding — nobody reads them there (the reference keeps no intermediate,
+        encoder.py:58-68).  The returned tensor is bit-identical either way."""
         x = _native.require_cuda(inputs, "inputs")
         if x.dim() != 4 or x.shape[-1] != 1:
             raise ValueError(f"inputs must be [B, T, F, 1] (encoder.py:51 squeezes the last axis); got {tuple(x.shape)}")
@@ -267,11 +276,16 @@ class Conv1DSubsamplingLayer:
                     raise NotImplementedError("padding='same' convs are not built (config/model.yaml:26 uses 'valid')")
                 t_out = max(0, get_conv_length(t_in, self.kernel_size[i], "valid", self.strides[i]))
                 cout = self.filters[i]
-                y = torch.empty((B, t_out, cout), dtype=torch.float32, device=x.device)
+                y = _native.empty((B, t_out, cout), torch.float32, x.device)
                 if B and t_out:
                     if use_tf32 and prefix_lengths and self.assume_zero_padding:
-                        _native.check(L.tasr_sepconv1d_tf32_ragged(self._plans[i], h.data_ptr(), lengths.data_ptr(), i,
-                                                                   B, t_in, y.data_ptr(), t_out, st))
+                        if lean_intermediates and i + 1 < len(self.kernel_size):
+                            _native.check(L.tasr_sepconv1d_tf32_ragged_lean(
+                                self._plans[i], h.data_ptr(), lengths.data_ptr(), i, B, t_in, y.data_ptr(), t_out,
+                                self.ragged_margin(), st))
+                        else:
+                            _native.check(L.tasr_sepconv1d_tf32_ragged(self._plans[i], h.data_ptr(), lengths.data_ptr(), i,
+                                                                       B, t_in, y.data_ptr(), t_out, st))
                     elif use_tf32:
                         _native.check(L.tasr_sepconv1d_tf32(self._plans[i], h.data_ptr(), B, t_in, y.data_ptr(), t_out, st))
                     else:

@@ -730,3 +730,52 @@ def test_captured_graph_refuses_stale_plans(cuda_device):
     fe.set_weights(oracle.glorot_subsampling_weights(192, 80, seed=8), cuda_device)
     with pytest.raises(RuntimeError, match="weights changed after capture"):
         cap.replay()
+
+
+def test_lean_intermediates_are_bit_identical_and_never_read_unwritten_rows(cuda_device):
+    """FrontEnd(lean_intermediates=True) leaves the far padding of the features and of the first two layers'
+    activations unwritten.  With every operator allocation poisoned with NaN first, the outputs must still equal
+    the fully materialised run bit for bit (so no kernel consumed an unwritten row), the written margin of the
+    features must be 0.0, and something must really have been left unwritten."""
+    from telugu_asr_b200.synth import draw_lengths
+    lens = draw_lengths(40, 1600, 240000, seed=11)
+    lens[0], lens[1], lens[2], lens[3], lens[4] = 240000, 399, 400, 20880, 41360   # max, no frame, one frame, tile edges
+    wav, ln = oracle.make_waveforms(lens, seed=11, dist="tilt")
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    w, l = gpu(wav, cuda_device), gpu(ln, cuda_device)
+    res = {}
+    for lean in (False, True):
+        fe = tasr.FrontEnd(math="tf32", lean_intermediates=lean)
+        fe.set_weights(weights, cuda_device)
+        _native.poison_allocations = True
+        try:
+            res[lean] = _call_or_skip(fe, w, l)
+            torch.cuda.synchronize()
+        finally:
+            _native.poison_allocations = False
+    for a, b in zip(res[True], res[False]):
+        assert torch.equal(a, b)
+    assert not torch.isnan(res[True][0]).any()
+    # the lean feature tensor on its own: data rows and n_frames identical, margin rows 0.0, far rows untouched
+    feat = tasr.SpeechFeaturizer(**tasr.REFERENCE_SPEECH_CONFIG)
+    margin = tasr.Conv1DSubsamplingLayer.ragged_margin()
+    assert margin >= 38
+    full, nf = feat.featurize_batch(w, l)
+    _native.poison_allocations = True
+    try:
+        lean_f, nf2 = feat.featurize_batch(w, l, pad_fill_rows=margin)
+        torch.cuda.synchronize()
+    finally:
+        _native.poison_allocations = False
+    assert torch.equal(nf, nf2)
+    untouched = 0
+    for b, t in enumerate(nf.cpu().tolist()):
+        assert torch.equal(lean_f[b, :t], full[b, :t])
+        hi = min(full.shape[1], t + margin)
+        assert not lean_f[b, t:hi].any()
+        untouched += int(torch.isnan(lean_f[b, hi:]).all(dim=(1, 2)).sum())
+    assert untouched > 10000   # most of the padding of this ragged batch was not written
+    # raw entry points validate their arguments
+    lib = _native.lib()
+    assert lib.tasr_logmel_f32_lean(feat._handle(cuda_device), w.data_ptr(), l.data_ptr(), None, 1, w.stride(0), full.data_ptr(),
+                                    full.shape[1], nf.data_ptr(), -1, _native.stream_ptr()) == _native.TASR_ERR_BAD_ARG
