@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--full-intermediates", action="store_true",
                     help="materialise the log-mel tensor and every layer's activations over the whole padded batch (A/B of the lean default)")
+    ap.add_argument("--two-pass", action="store_true",
+                    help="separate tasr_absmax_f32 pass before the log-mel kernel (A/B of the single-pass default)")
     ap.add_argument("--streams", type=int, default=2, help="batches in flight (CUDA-graph replays on this many streams)")
     return ap.parse_args()
 
@@ -271,7 +273,7 @@ def main():
     fe = None
     if math_mode in ("auto", "tf32"):
         try:
-            fe = tasr.FrontEnd(math="tf32", lean_intermediates=not args.full_intermediates)
+            fe = tasr.FrontEnd(math="tf32", lean_intermediates=not args.full_intermediates, single_pass=not args.two_pass)
             fe.set_weights(weights, dev)
             fe.subsampling._ensure_plans()
             math_mode = "tf32"

@@ -144,6 +144,28 @@ int tasr_logmel_f32_lean(const TasrFeaturizer* f, const float* wav, const int32_
                          const float* peak_or_null, int32_t batch, int64_t row_stride, float* out,
                          int32_t t_max, int32_t* n_frames, int32_t pad_fill_rows, tasr_stream_t stream);
 
+/* Single-pass variant (the waveform is read ONCE; tasr_absmax_f32 is not needed): the kernel accumulates
+ * peak_out[b] = max|x_b| while it stages the samples, featurises the UN-normalised signal and applies no floor, so
+ * out holds log(mel power of x) — -inf where that power is 0.  Because the featurizer is scale-covariant,
+ *   log-mel(x / (peak + 1e-9))[t, m] = max( out[t, m] + 2*log(1 / (peak + 1e-9)),  log(output_floor) )
+ * (src/speech_featurizer.py:68-72, 107-110), which the READER applies: tasr_sepconv1d_tf32_ragged_lean takes the
+ * TasrDeferredGain this call fills in (host struct, device peak pointer), tasr_apply_deferred_gain materialises the
+ * reference's feature values in place.  Differences to the two-pass result are float32 rounding only (the gain is
+ * applied after the arithmetic instead of before it).  pad_fill_rows as in tasr_logmel_f32_lean (< 0: all rows).
+ * Needs normalize_signal = 1, pad_end = 0, feature_type log-mel or spectrogram, no per-frame normalisation. */
+typedef struct TasrDeferredGain {
+  const float* peak;   /* device [batch]: max|x_b|                                   */
+  float log_scale_x2;  /* 2*log10(2) or 2*ln(2): the gain enters the power squared   */
+  float log_floor;     /* log(output_floor) in the handle's base                     */
+} TasrDeferredGain;
+int tasr_logmel_f32_single_pass(const TasrFeaturizer* f, const float* wav, const int32_t* len, int32_t batch,
+                                int64_t row_stride, float* out, int32_t t_max, int32_t* n_frames,
+                                int32_t pad_fill_rows, float* peak_out, TasrDeferredGain* gain_host,
+                                tasr_stream_t stream);
+/* feat[b, t, :] = max(feat[b, t, :] + 2*log(1/(peak[b]+1e-9)), log_floor) for t < n_frames[b], in place. */
+int tasr_apply_deferred_gain(float* feat, const int32_t* n_frames, int32_t batch, int32_t t_max, int32_t f,
+                             const TasrDeferredGain* gain_host, tasr_stream_t stream);
+
 /* Replaces one tf.keras.layers.SeparableConv1D forward (encoder.py:31-40, called at :60):
  * y[b,t,o] = act( sum_c ( sum_k x[b, stride*t+k, c] * dw[k,c] ) * pw[c,o] + bias[o] ),
  * "valid" padding, t < t_out where t_out <= (t_in-kernel)/stride+1.  x [batch,t_in,c_in],
@@ -177,13 +199,16 @@ int tasr_sepconv1d_tf32_ragged(const TasrSepConvPlan* plan, const float* x, cons
 /* Lean variant for an INTERMEDIATE activation tensor whose only reader is the next ragged layer of the stack
  * (src/models/moonshine/encoder.py:58-68 keeps no intermediate): of the rows that only repeat the constant padding
  * row — t >= ceil(len0[b] / 2^(shift+1)) — at least the first fill_rows are written (whole 128-row tiles), the
- * tiles beyond are left untouched.  All other rows are identical to tasr_sepconv1d_tf32_ragged.
+ * tiles beyond are left untouched (fill_rows < 0: every row is written).  All other rows are identical to
+ * tasr_sepconv1d_tf32_ragged.
  * tasr_sepconv_ragged_margin() is the number of input rows past ceil(len0[b] / 2^shift) that the ragged kernels
  * may read: a producer in lean mode must be given fill_rows / pad_fill_rows >= that. */
 int32_t tasr_sepconv_ragged_margin(void);
 int tasr_sepconv1d_tf32_ragged_lean(const TasrSepConvPlan* plan, const float* x, const int32_t* len0, int32_t shift,
                                     int32_t batch, int32_t t_in, float* y, int32_t t_out, int32_t fill_rows,
-                                    tasr_stream_t stream);
+                                    const TasrDeferredGain* input_gain_or_null, tasr_stream_t stream);
+/* input_gain_or_null (host struct; first layer only, shift == 0): x comes from tasr_logmel_f32_single_pass and every
+ * row t < len0[b] is read as max(x + 2*log(1/(peak[b]+1e-9)), log_floor); fill_rows < 0 writes every row of y. */
 
 /* Replaces math_util.get_conv_length applied per layer (src/utils/math_util.py:20-32,
  * encoder.py:60-68) and lengths_to_padding_mask (encoder.py:43-48).

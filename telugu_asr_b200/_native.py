@@ -29,6 +29,10 @@ class TasrFeatParams(C.Structure):
 FEATURE_TYPES = {"log_mel_spectrogram": 0, "spectrogram": 1, "mfcc": 2, "waveform": 3}
 
 
+class TasrDeferredGain(C.Structure):
+    _fields_ = [("peak", C.c_void_p), ("log_scale_x2", C.c_float), ("log_floor", C.c_float)]
+
+
 class TasrSepConvLayer(C.Structure):
     _fields_ = [
         ("dw", C.c_void_p), ("pw", C.c_void_p), ("bias", C.c_void_p),
@@ -51,6 +55,9 @@ _SIGNATURES = {
     "tasr_absmax_f32": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "tasr_logmel_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _vp, _vp]),
     "tasr_logmel_f32_lean": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _vp, _i32, _vp]),
+    "tasr_logmel_f32_single_pass": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _i32, _vp, _i32, _vp,
+                                              C.POINTER(TasrDeferredGain), _vp]),
+    "tasr_apply_deferred_gain": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.POINTER(TasrDeferredGain), _vp]),
     "tasr_sepconv1d_f32": (C.c_int, [_vp, _i32, _i32, C.POINTER(TasrSepConvLayer), _vp, _i32, _vp]),
     "tasr_sepconv_plan_create": (C.c_int, [C.POINTER(TasrSepConvLayer), C.POINTER(_vp), _vp]),
     "tasr_sepconv_plan_destroy": (C.c_int, [_vp]),
@@ -59,7 +66,8 @@ _SIGNATURES = {
     "tasr_sepconv_plan_pad_row": (C.c_void_p, [_vp]),
     "tasr_sepconv1d_tf32_ragged": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp]),
     "tasr_sepconv_ragged_margin": (C.c_int32, []),
-    "tasr_sepconv1d_tf32_ragged_lean": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp]),
+    "tasr_sepconv1d_tf32_ragged_lean": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32,
+                                                  C.POINTER(TasrDeferredGain), _vp]),
     "tasr_conv_lengths_mask": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32),
                                          C.POINTER(_i32), _vp, _vp, _i32, _vp]),
     "tasr_specaugment_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp]),

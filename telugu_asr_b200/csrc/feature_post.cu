@@ -124,6 +124,33 @@ int tasr_feature_post_launch(const TasrFeaturizer* f, float* feat, const int32_t
   return TASR_OK;
 }
 
+namespace {
+__global__ void apply_gain_kernel(float* __restrict__ feat, const int32_t* __restrict__ n_frames, int T_max, int F,
+                                  const float* __restrict__ peak, float scale2, float floor_) {
+  const int b = blockIdx.y;
+  const int n = min(n_frames[b], T_max) * F;
+  float lg;
+  const float g = __fdiv_rn(1.0f, __fadd_rn(peak[b], 1e-9f));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(g));
+  const float c = scale2 * lg;
+  float* row = feat + (size_t)b * T_max * F;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) row[i] = fmaxf(row[i] + c, floor_);
+}
+}  // namespace
+
+extern "C" int tasr_apply_deferred_gain(float* feat, const int32_t* n_frames, int32_t B, int32_t T_max, int32_t F,
+                                        const TasrDeferredGain* gain, tasr_stream_t stream) {
+  if (!feat || !n_frames || !gain || !gain->peak) return fail(TASR_ERR_BAD_ARG, "tasr_apply_deferred_gain: null argument");
+  if (B < 0 || T_max < 0 || F < 0) return fail(TASR_ERR_BAD_ARG, "tasr_apply_deferred_gain: negative size");
+  if (B == 0 || T_max == 0 || F == 0) return TASR_OK;
+  if (B > 65535) return fail(TASR_ERR_UNSUPPORTED, "tasr_apply_deferred_gain: batch > 65535");
+  const long long per = ((long long)T_max * F + 255) / 256;
+  dim3 grid((unsigned)(per > 64 ? 64 : per), (unsigned)B);
+  apply_gain_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feat, n_frames, T_max, F, gain->peak, gain->log_scale_x2, gain->log_floor);
+  TASR_LAUNCH_CHECK("apply_gain_kernel");
+  return TASR_OK;
+}
+
 extern "C" int tasr_waveform_f32(const TasrFeaturizer* f, const float* wav, const int32_t* len, const float* peak,
                                  int32_t B, int64_t row_stride, float* out, tasr_stream_t stream) {
   if (!f || !wav || !len || !out) return fail(TASR_ERR_BAD_ARG, "tasr_waveform_f32: null argument");

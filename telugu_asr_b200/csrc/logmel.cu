@@ -28,6 +28,7 @@
 // persistent loop.  Twiddles are float64-derived tables.
 #include "logmel_common.cuh"
 #include <stdlib.h>
+#include <math.h>
 
 using namespace tasr;
 
@@ -233,7 +234,7 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
       const int count = (nvalid - 1) * kFrameStep + kFrameLen;  // multiple of 4; s0+count <= n unless pad_end
       const int lim = a.pad_end ? min(count, n - s0) : count;   // samples of the tile that exist
       float g = 1.0f;
-      if (a.normalize) g = __fdiv_rn(1.0f, __fadd_rn(a.peak[b], 1e-9f));  // :70
+      if (a.normalize && a.peak_out == nullptr) g = __fdiv_rn(1.0f, __fadd_rn(a.peak[b], 1e-9f));  // :70
       const float c = a.preemph;
       float4 x[kWavSlots];
       float xp[kWavSlots];
@@ -247,6 +248,26 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
           x[u] = *reinterpret_cast<const float4*>(row + s);   // (rows are padded to 4 samples: in bounds)
           if (s > 0) xp[u] = row[s - 1];
         }
+      }
+      if (a.peak_out != nullptr) {
+        // Single pass: max|x| of the samples this tile stages (slots beyond `lim` hold zeros); the tile that holds the
+        // utterance's last frame also takes the samples no frame covers, [s0+count, n).  Non-negative floats order like
+        // their bit patterns, so the warp maximum is one integer REDUX and the merge one atomicMax per warp.
+        float m = 0.0f;
+#pragma unroll
+        for (int u = 0; u < kWavSlots; ++u)
+          m = fmaxf(fmaxf(m, fmaxf(fabsf(x[u].x), fabsf(x[u].y))), fmaxf(fabsf(x[u].z), fabsf(x[u].w)));
+        if (f0 + nvalid >= Tb) {
+          for (int i = s0 + count + 4 * tid; i < n; i += 4 * kThreads) {
+            const float4 t4 = *reinterpret_cast<const float4*>(row + i);
+            m = fmaxf(m, fabsf(t4.x));
+            if (i + 1 < n) m = fmaxf(m, fabsf(t4.y));
+            if (i + 2 < n) m = fmaxf(m, fabsf(t4.z));
+            if (i + 3 < n) m = fmaxf(m, fabsf(t4.w));
+          }
+        }
+        const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+        if (lane == 0 && mb != 0u) atomicMax(reinterpret_cast<unsigned*>(a.peak_out) + b, mb);
       }
 #pragma unroll
       for (int u = 0; u < kWavSlots; ++u) {
@@ -398,10 +419,11 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
 
 static int logmel_launch(const TasrFeaturizer* f, const float* wav, const int32_t* len,
                          const float* peak, int32_t B, int64_t row_stride, float* out,
-                         int32_t T_max, int32_t* n_frames, int32_t pad_fill_rows, tasr_stream_t stream) {
+                         int32_t T_max, int32_t* n_frames, int32_t pad_fill_rows, tasr_stream_t stream,
+                         float* peak_out = nullptr) {
   if (!f || !wav || !len || !out || !n_frames) return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32: null argument");
   if (B < 0 || T_max < 0 || row_stride < 0) return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32: negative size");
-  if (f->p.normalize_signal && !peak)
+  if (f->p.normalize_signal && !peak && !peak_out)
     return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32: normalize_signal is set but peak is NULL (run tasr_absmax_f32 first)");
   if (!aligned16(wav) || (row_stride & 3) || !aligned16(out))
     return fail(TASR_ERR_MISALIGNED, "tasr_logmel_f32: wav/out must be 16-byte aligned and row_stride a multiple of 4 samples");
@@ -424,7 +446,7 @@ static int logmel_launch(const TasrFeaturizer* f, const float* wav, const int32_
     attr_set[dev] = true;
   }
   LogmelArgs a;
-  a.wav = wav; a.len = len; a.peak = peak; a.out = out; a.n_frames = n_frames;
+  a.wav = wav; a.len = len; a.peak = peak; a.out = out; a.n_frames = n_frames; a.peak_out = peak_out;
   a.hwin = f->d_hwin; a.tw256 = f->d_tw256; a.tw512 = f->d_tw512; a.band_w = f->d_band_w; a.bands = f->d_bands;
   a.row_stride = row_stride; a.B = B; a.T_max = T_max; a.tiles_per_row = tiles_per_row;
   a.normalize = f->p.normalize_signal ? 1 : 0;
@@ -432,6 +454,10 @@ static int logmel_launch(const TasrFeaturizer* f, const float* wav, const int32_
   a.mode = (f->p.feature_type == TASR_FEAT_SPECTROGRAM) ? 1 : 0;
   a.pad_fill_rows = pad_fill_rows;
   a.preemph = f->p.preemphasis; a.floor_ = f->p.output_floor; a.log_scale = f->log_scale;
+  if (peak_out) {
+    a.floor_ = 0.0f;   // the floor is applied by the reader, after the gain (lg2(0) = -inf survives the addition)
+    TASR_CUDA(cudaMemsetAsync(peak_out, 0, (size_t)B * sizeof(float), st));
+  }
   // Persistent grid: two CTAs per SM; never more CTAs than work items (valid tiles + padding chunks <= total + B).
   const long long cap = total + B;
   static const int ctas_per_sm = [] { const char* e = getenv("TASR_LOGMEL_CTAS_PER_SM"); const int v = e ? atoi(e) : 2; return v >= 1 && v <= 2 ? v : 2; }();
@@ -463,6 +489,21 @@ extern "C" int tasr_logmel_f32_lean(const TasrFeaturizer* f, const float* wav, c
   if (f && (f->p.feature_type == TASR_FEAT_MFCC || f->p.normalize_zscore || f->p.normalize_min_max))
     return fail(TASR_ERR_UNSUPPORTED, "tasr_logmel_f32_lean: mfcc / per-frame normalisation post-process the whole tensor; use tasr_logmel_f32");
   return logmel_launch(f, wav, len, peak, B, row_stride, out, T_max, n_frames, pad_fill_rows, stream);
+}
+
+extern "C" int tasr_logmel_f32_single_pass(const TasrFeaturizer* f, const float* wav, const int32_t* len, int32_t B,
+                                           int64_t row_stride, float* out, int32_t T_max, int32_t* n_frames,
+                                           int32_t pad_fill_rows, float* peak_out, TasrDeferredGain* gain_host,
+                                           tasr_stream_t stream) {
+  if (!f || !peak_out || !gain_host) return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32_single_pass: null argument");
+  if (!f->p.normalize_signal)
+    return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32_single_pass: the handle does not normalise the signal; use tasr_logmel_f32");
+  if (f->p.pad_end || f->p.feature_type == TASR_FEAT_MFCC || f->p.normalize_zscore || f->p.normalize_min_max)
+    return fail(TASR_ERR_UNSUPPORTED, "tasr_logmel_f32_single_pass: pad_end / mfcc / per-frame normalisation need the two-pass tasr_logmel_f32");
+  gain_host->peak = peak_out;
+  gain_host->log_scale_x2 = 2.0f * f->log_scale;
+  gain_host->log_floor = f->p.log_base_e ? logf(f->p.output_floor) : log10f(f->p.output_floor);
+  return logmel_launch(f, wav, len, nullptr, B, row_stride, out, T_max, n_frames, pad_fill_rows, stream, peak_out);
 }
 
 // Host side of the fixed-geometry check (called by tasr_featurizer_create): fills wr/wf from the dense

@@ -42,6 +42,9 @@ struct LogmelArgs {
   const float* wav;
   const int32_t* len;
   const float* peak;       // may be null when !normalize
+  float* peak_out;         // single-pass mode (non-null): the kernel itself accumulates max|x| per utterance here (zeroed
+                           // by the launcher), runs on the UN-normalised signal and applies no floor; the reader adds
+                           // 2*log(1/(peak+1e-9)) and clamps (TasrDeferredGain)
   float* out;
   int32_t* n_frames;
   const float* hwin;

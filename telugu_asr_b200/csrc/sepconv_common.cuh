@@ -166,6 +166,10 @@ struct SepArgs {
   // i < fill_rows, rounded up to whole tiles — are guaranteed to be written; tiles beyond are left untouched
   // (for an intermediate tensor whose only reader is the next ragged layer).  < 0: every row is written.
   int32_t fill_rows;
+  // deferred input gain (in_peak != nullptr; first layer after tasr_logmel_f32_single_pass): a row t < cf of x is read as
+  // max(x + in_scale2 * lg2(1 / (in_peak[b] + 1e-9)), in_floor)
+  const float* in_peak;
+  float in_scale2, in_floor;
 };
 
 }  // namespace tasr_sep

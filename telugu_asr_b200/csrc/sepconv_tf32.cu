@@ -72,6 +72,17 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
     }
   }
 
+  // deferred input gain of the single-pass featurizer (CTA-uniform): c = 2*log(g), g = 1/(peak+1e-9) as the reference
+  // rounds it (src/speech_featurizer.py:70)
+  const bool fix = (a.in_peak != nullptr);
+  float gc = 0.0f;
+  if (fix) {
+    float lg;
+    const float g = __fdiv_rn(1.0f, __fadd_rn(a.in_peak[b], 1e-9f));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(g));
+    gc = a.in_scale2 * lg;
+  }
+
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   if (tid == 32) {
     for (int i = 0; i < 5; ++i) mbar_init(bar_u + 8 * i, 1);
@@ -131,6 +142,15 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
         v[i] = (cok && r0 + i < a.T_in) ? __ldg(xrow + c0 + (size_t)i * C_in) : 0.0f;
 #pragma unroll
       for (int k = 0; k < 9; ++k) w[k] = cok ? __ldg(a.dw + k * C_in + c0 + lane) : 0.0f;
+    }
+    if (fix) {                            // rows of the data get the gain and the floor; padding rows stay 0.0
+      if (r0 + kWin <= cf) {
+#pragma unroll
+        for (int i = 0; i < kWin; ++i) v[i] = fmaxf(v[i] + gc, a.in_floor);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kWin; ++i) v[i] = (r0 + i < cf) ? fmaxf(v[i] + gc, a.in_floor) : v[i];
+      }
     }
     }
     if (tid == 0 && kc >= 1 && kc + 1 < a.n_chunks) {   // (the loads above are in flight while this waits)
@@ -314,7 +334,8 @@ extern "C" int tasr_sepconv_plan_destroy(TasrSepConvPlan* p) {
 }
 
 static int launch_tf32(const char* who, const TasrSepConvPlan* p, const float* x, const int32_t* len0, int32_t shift,
-                       int32_t B, int32_t T_in, float* y, int32_t T_out, tasr_stream_t stream, int32_t fill_rows = -1) {
+                       int32_t B, int32_t T_in, float* y, int32_t T_out, tasr_stream_t stream, int32_t fill_rows = -1,
+                       const TasrDeferredGain* gain = nullptr) {
   if (!p) return fail(TASR_ERR_BAD_ARG, "%s: null plan", who);
   int rc = validate_sepconv(who, x, B, T_in, &p->L, y, T_out);
   if (rc != TASR_OK) return rc;
@@ -327,7 +348,10 @@ static int launch_tf32(const char* who, const TasrSepConvPlan* p, const float* x
   a.T_in = T_in; a.T_out = T_out; a.C_in = p->L.c_in; a.C_out = p->L.c_out; a.NT = p->NT;
   a.n_chunks = p->n_chunks; a.act = p->L.activation;
   a.len0 = len0; a.pad_out = p->d_pad_out; a.shift = shift; a.fill_rows = fill_rows;
-  if (p->use_ws) {                       // (the persistent kernel always writes every row: fill_rows is a permission)
+  a.in_peak = gain ? gain->peak : nullptr;
+  a.in_scale2 = gain ? gain->log_scale_x2 : 0.0f;
+  a.in_floor = gain ? gain->log_floor : 0.0f;
+  if (p->use_ws && !gain) {                       // (the persistent kernel always writes every row: fill_rows is a permission)
     const int wrc = tasr_sepconv_ws_launch(p, a, B, (cudaStream_t)stream);
     if (wrc >= 0) return wrc;            // launched (TASR_OK) or failed with an error code
   }
@@ -375,11 +399,12 @@ extern "C" int32_t tasr_sepconv_ragged_margin(void) { return kWin; }
 
 extern "C" int tasr_sepconv1d_tf32_ragged_lean(const TasrSepConvPlan* p, const float* x, const int32_t* len0, int32_t shift,
                                                int32_t B, int32_t T_in, float* y, int32_t T_out, int32_t fill_rows,
-                                               tasr_stream_t stream) {
+                                               const TasrDeferredGain* gain, tasr_stream_t stream) {
   if (!p || !len0) return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32_ragged_lean: null argument");
   if (shift < 0 || shift > 29) return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32_ragged_lean: shift must be in [0,29]");
-  if (fill_rows < 0) return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32_ragged_lean: fill_rows must be >= 0 (use tasr_sepconv1d_tf32_ragged to write every row)");
+  if (gain && (shift != 0 || !gain->peak))
+    return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32_ragged_lean: a deferred input gain belongs to the first layer (shift 0) and needs a peak pointer");
   if (!p->pad_ready)
     return fail(TASR_ERR_BAD_ARG, "tasr_sepconv1d_tf32_ragged_lean: call tasr_sepconv_plan_set_pad_row first (the input's padding row is unknown)");
-  return launch_tf32("tasr_sepconv1d_tf32_ragged_lean", p, x, len0, shift, B, T_in, y, T_out, stream, fill_rows);
+  return launch_tf32("tasr_sepconv1d_tf32_ragged_lean", p, x, len0, shift, B, T_in, y, T_out, stream, fill_rows < 0 ? -1 : fill_rows, gain);
 }

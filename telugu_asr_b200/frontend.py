@@ -45,7 +45,7 @@ def load_reference_yaml(path: str):
 class FrontEnd:
     def __init__(self, speech_config: dict | None = None, subsampling_config: dict | None = None,
                  model_dim: int = REFERENCE_D_MODEL, math: str = "tf32", device=None, seed: int = 0,
-                 lean_intermediates: bool = True):
+                 lean_intermediates: bool = True, single_pass: bool = True):
         self.featurizer = SpeechFeaturizer(**(speech_config or REFERENCE_SPEECH_CONFIG))
         self.subsampling = Conv1DSubsamplingLayer(
             model_dim=model_dim, subsampling_config=subsampling_config or REFERENCE_SUBSAMPLING_CONFIG,
@@ -55,6 +55,12 @@ class FrontEnd:
         # collate padding nobody reads them (the ragged layers treat those rows as one constant row), so they are
         # not written there.  Outputs are bit-identical; `return_features=True` always gets the full 0.0 padding.
         self.lean_intermediates = bool(lean_intermediates)
+        # normalize_signal needs max|x| of the whole utterance before its first frame (src/speech_featurizer.py:68-72):
+        # a second pass over the waveform.  The featurizer is scale-covariant, so the log-mel kernel can find the
+        # peak while it reads the samples, work on the un-normalised signal, and let the first separable conv add
+        # 2 log(gain) and the floor as it reads the features (float32 rounding differences only).  Used when the
+        # features are not returned; `return_features=True` takes the two-pass path and gets the reference values.
+        self.single_pass = bool(single_pass)
 
     def set_weights(self, weights, device=None):
         self.subsampling.set_weights(weights, device or self.device)
@@ -73,10 +79,17 @@ class FrontEnd:
         sub = self.subsampling
         lean = (self.lean_intermediates and sub.math == "tf32" and sub.assume_zero_padding
                 and all(p == "valid" for p in sub.padding))
-        feats, n_frames = self.featurizer.featurize_batch(
-            wav, lengths, t_max=t_max, pad_fill_rows=sub.ragged_margin() if (lean and not return_features) else None)
+        ragged = sub.math == "tf32" and sub.assume_zero_padding and all(p == "valid" for p in sub.padding)
+        fill = sub.ragged_margin() if (lean and not return_features) else None
+        gain = None
+        if (self.single_pass and ragged and not return_features and self.featurizer.supports_single_pass()
+                and self.featurizer.feature_type == "log_mel_spectrogram"):
+            feats, n_frames, gain = self.featurizer.featurize_batch(wav, lengths, t_max=t_max, pad_fill_rows=fill, single_pass=True)
+        else:
+            feats, n_frames = self.featurizer.featurize_batch(wav, lengths, t_max=t_max, pad_fill_rows=fill)
         out, mask, len_all = sub(feats, mask=n_frames, return_lengths=True,
-                                 max_frames=t_max if max_length is not None else None, lean_intermediates=lean)
+                                 max_frames=t_max if max_length is not None else None, lean_intermediates=lean,
+                                 input_gain=gain)
         len3 = len_all[-1]
         if return_features:
             return out, mask, len3, feats, n_frames

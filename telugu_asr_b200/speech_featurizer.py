@@ -33,6 +33,15 @@ class FeaturizerConfig:  # src/speech_featurizer.py:10-15
     mfcc: str = "mfcc"
 
 
+class DeferredGain:
+    """What `featurize_batch(single_pass=True)` hands to the reader of its raw features: the device tensor of
+    per-utterance peaks and the host struct (TasrDeferredGain) the C entry points take."""
+
+    def __init__(self, peak: torch.Tensor):
+        self.peak = peak
+        self.struct = _native.TasrDeferredGain(peak=peak.data_ptr(), log_scale_x2=0.0, log_floor=0.0)
+
+
 class SpeechFeaturizer:
     def __init__(
         self,
@@ -212,14 +221,34 @@ class SpeechFeaturizer:
         out = out[:, :n_max]
         return out[0] if one else out
 
+    def supports_single_pass(self) -> bool:
+        return bool(self._normalize_signal and not self.pad_end and not self._normalize_zscore and not self._normalize_min_max
+                    and self.feature_type in (FeaturizerConfig.log_mel_spectrogram, FeaturizerConfig.spectrogram))
+
+    def apply_deferred_gain(self, raw: torch.Tensor, n_frames: torch.Tensor, gain: "DeferredGain") -> torch.Tensor:
+        """In place: raw [B, T, F(,1)] from `featurize_batch(single_pass=True)` -> the reference's feature values
+        max(raw + 2 log(1/(peak+1e-9)), log(output_floor)) on rows t < n_frames[b]."""
+        _native.require_cuda(raw, "raw")
+        B, T, F = raw.shape[0], raw.shape[1], raw.shape[2]
+        with torch.cuda.device(raw.device):
+            _native.check(_native.lib().tasr_apply_deferred_gain(raw.data_ptr(), n_frames.data_ptr(), B, T, F,
+                                                                 C.byref(gain.struct), _native.stream_ptr()))
+        return raw
+
     # ------------------------------------------------------------------ batched device path
     def featurize_batch(self, wav: torch.Tensor, lengths: torch.Tensor | None, out: torch.Tensor | None = None,
-                        t_max: int | None = None, pad_fill_rows: int | None = None):
+                        t_max: int | None = None, pad_fill_rows: int | None = None, single_pass: bool = False):
         """wav [B, N_max] float32 CUDA (rows zero padded; padding is never read), lengths [B] int32
         CUDA -> (features [B, T_max, F, 1] with rows >= n_frames[b] equal to 0.0, n_frames [B] int32).
         T_max defaults to get_nframes(N_max) clamped at 0, i.e. the collate's batch maximum.
         `pad_fill_rows` (lean mode, for a feature tensor that only feeds the ragged subsampling): write just that
-        many 0.0 rows past each utterance's frames and leave the rest of the collate padding untouched."""
+        many 0.0 rows past each utterance's frames and leave the rest of the collate padding untouched.
+        `single_pass` (see `supports_single_pass`): the waveform is read once — the kernel finds max|x| itself and
+        featurises the un-normalised signal; returns (raw_features, n_frames, DeferredGain), and the reader
+        (Conv1DSubsamplingLayer(input_gain=...) or `apply_deferred_gain`) adds the gain and the floor."""
+        if single_pass and not self.supports_single_pass():
+            raise ValueError("single_pass needs normalize_signal=True, pad_end=False, a log-mel or spectrogram featurizer "
+                             "and no per-frame normalisation")
         _native.require_cuda(wav, "wav")
         dev = wav.device
         B, n_max = wav.shape
@@ -251,16 +280,34 @@ class SpeechFeaturizer:
             if tuple(out.shape) != (B, t_max, F, 1) or not out.is_contiguous() or out.dtype != torch.float32:
                 raise ValueError(f"out must be a contiguous float32 [B={B}, T_max={t_max}, {F}, 1] tensor")
         n_frames = torch.empty((B,), dtype=torch.int32, device=dev)
+        gain = None
+        if single_pass:
+            gain = DeferredGain(_native.empty((B,), torch.float32, dev))
         if B == 0:
-            return out, n_frames
+            return (out, n_frames, gain) if single_pass else (out, n_frames)
         if t_max == 0:   # nothing to featurise: every utterance is shorter than one frame
-            return out, n_frames.zero_()
+            if single_pass:
+                gain.peak.zero_()
+            return (out, n_frames.zero_(), gain) if single_pass else (out, n_frames.zero_())
         h = self._handle(dev)
         L = _native.lib()
         with torch.cuda.device(dev):
             st = _native.stream_ptr()
             peak_ptr = None
             _native.mark("begin")
+            if single_pass:
+                ev = self.profile_events
+                if ev is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                _native.check(L.tasr_logmel_f32_single_pass(
+                    h, wav.data_ptr(), lengths.data_ptr(), B, row_stride, out.data_ptr(), t_max, n_frames.data_ptr(),
+                    -1 if pad_fill_rows is None else int(pad_fill_rows), gain.peak.data_ptr(), C.byref(gain.struct), st))
+                if ev is not None:
+                    e1.record()
+                    ev.append((e0, e1))
+                _native.mark("logmel_kernel")
+                return out, n_frames, gain
             if self._normalize_signal:
                 peak = torch.empty((B,), dtype=torch.float32, device=dev)
                 _native.check(L.tasr_absmax_f32(wav.data_ptr(), lengths.data_ptr(), B, row_stride, peak.data_ptr(), st))

@@ -229,10 +229,12 @@ class Conv1DSubsamplingLayer:
         return int(_native.lib().tasr_sepconv_ragged_margin())
 
     def __call__(self, inputs: torch.Tensor, training: bool = False, mask=None, return_lengths: bool = False,
-                 max_frames: int | None = None, lean_intermediates: bool = False):
+                 max_frames: int | None = None, lean_intermediates: bool = False, input_gain=None):
         """`lean_intermediates` (ragged TF32 path only): the outputs of all layers but the last are not
         materialised far inside the padding — nobody reads them there (the reference keeps no intermediate,
-        encoder.py:58-68).  The returned tensor is bit-identical either way."""
+        encoder.py:58-68).  The returned tensor is bit-identical either way.
+        `input_gain` (a speech_featurizer.DeferredGain): `inputs` are the raw features of
+        `featurize_batch(single_pass=True)`; the first layer adds the gain and the floor as it reads them."""
         x = _native.require_cuda(inputs, "inputs")
         if x.dim() != 4 or x.shape[-1] != 1:
             raise ValueError(f"inputs must be [B, T, F, 1] (encoder.py:51 squeezes the last axis); got {tuple(x.shape)}")
@@ -266,6 +268,8 @@ class Conv1DSubsamplingLayer:
                 raise ValueError("mask must be lengths [B], [B,T] or [B,T,F]")
 
         use_tf32 = self.math == "tf32"
+        if input_gain is not None and not (use_tf32 and prefix_lengths and self.assume_zero_padding):
+            raise ValueError("input_gain needs the ragged TF32 path: math='tf32', assume_zero_padding=True and mask=n_frames [B]")
         if use_tf32:
             self._ensure_plans()
         with torch.cuda.device(x.device):
@@ -279,10 +283,13 @@ class Conv1DSubsamplingLayer:
                 y = _native.empty((B, t_out, cout), torch.float32, x.device)
                 if B and t_out:
                     if use_tf32 and prefix_lengths and self.assume_zero_padding:
-                        if lean_intermediates and i + 1 < len(self.kernel_size):
+                        lean_i = lean_intermediates and i + 1 < len(self.kernel_size)
+                        gain_i = input_gain if i == 0 else None
+                        if lean_i or gain_i is not None:
                             _native.check(L.tasr_sepconv1d_tf32_ragged_lean(
                                 self._plans[i], h.data_ptr(), lengths.data_ptr(), i, B, t_in, y.data_ptr(), t_out,
-                                self.ragged_margin(), st))
+                                self.ragged_margin() if lean_i else -1,
+                                C.byref(gain_i.struct) if gain_i is not None else None, st))
                         else:
                             _native.check(L.tasr_sepconv1d_tf32_ragged(self._plans[i], h.data_ptr(), lengths.data_ptr(), i,
                                                                        B, t_in, y.data_ptr(), t_out, st))
