@@ -367,20 +367,29 @@ def main():
     for s in range(2):
         pipe.stage(s, utts)                 # host packing is the loader's job: outside the timed region
     e2e_steps = max(3, min(args.steps, 100))
-    for i in range(4):
+    for i in range(8):
         tk = pipe.submit(i % 2)
     tk.wait()
     barrier()
-    l0 = lib.tasr_launch_count()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for i in range(e2e_steps):
-        tk = pipe.submit(i % 2)
-    pipe.s_out.synchronize()                # last D2H has landed
-    g1.record()
-    barrier()
-    e2e_ms = g0.elapsed_time(g1)
-    e2e_launches = int(lib.tasr_launch_count() - l0)
+    e2e_windows = []
+    for w_ in range(3 if os.environ.get("TASR_E2E_WINDOWS") else 1):
+        n_alloc0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+        l0 = lib.tasr_launch_count()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_host0 = time.perf_counter()
+        g0.record()
+        for i in range(e2e_steps):
+            tk = pipe.submit(i % 2)
+        t_host1 = time.perf_counter()
+        pipe.drain()                            # last D2H has landed
+        g1.record()
+        barrier()
+        e2e_ms = g0.elapsed_time(g1)
+        e2e_launches = int(lib.tasr_launch_count() - l0)
+        if pipe.graph:                          # replayed kernels do not pass through the C ABI counter
+            e2e_launches = int(pipe.kernels_per_submit) * e2e_steps
+        e2e_windows.append({"ms_per_step": e2e_ms / e2e_steps, "host_submit_ms_per_step": (t_host1 - t_host0) * 1e3 / e2e_steps,
+                            "cudaMallocs": int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - n_alloc0)})
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     h_o, h_m, h_l = tk.wait()
     enc, mask, len3 = out
@@ -513,11 +522,12 @@ def main():
                          "note": "HBM is the contract bound (SURVEY.md 8d); the kernel is latency-bound at 16 resident warps/SM (61 % issue, 39 % FMA pipe, 18 % DRAM in ncu; an FP32x2 variant with 31 % fewer instructions takes the same time), see DESIGN.md 4.2; kernel_ms is its single-stream time, the step overlaps two batches"},
             "e2e": {"value": e2e_val, "unit": "audio-seconds/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps, "gpu_launches": e2e_launches,
-                    "matches_device_resident_result": e2e_ok,
+                    "matches_device_resident_result": e2e_ok, "windows": e2e_windows,
                     "pcie_h2d_gbs": h2d / (e2e_ms_max / e2e_steps * 1e-3) / 1e9,
                     "api": "telugu_asr_b200.FrontEndPipeline.submit: ragged int16 PCM in pinned host memory (valid samples only) -> "
                            "H2D -> unpack -> peak -> log-mel -> 3x sepconv -> lengths/mask -> D2H of [B,T3,192] f32 + mask + len3; "
-                           "three streams, double-buffered slots",
+                           "three streams, double-buffered slots; the device side of a submit (unpack, front end, D2H) is one "
+                           "CUDA-graph launch per slot",
                     "f32_padded_single_stream": {"value": audio_s / (pad_ms * 1e-3), "ms_per_step": pad_ms,
                                                  "h2d_bytes_per_step": int(pb.h2d_bytes), "note": "rank 0; padded float32 [B,N_max] H2D, no overlap"}},
             "stages": stages,

@@ -860,3 +860,43 @@ def test_single_pass_frontend_matches_two_pass_and_oracle(cuda_device):
     feat = tasr.SpeechFeaturizer(**{**tasr.REFERENCE_SPEECH_CONFIG, "normalize_signal": False})
     with pytest.raises(ValueError):
         feat.featurize_batch(w, l, single_pass=True)
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_host_to_host_pipeline_matches_device_front_end(cuda_device, graph):
+    """FrontEndPipeline (pinned int16 PCM in, encoder input + mask + lengths back in pinned host memory), eager and
+    as one CUDA-graph launch per slot: three different ragged batches through two slots, each result bit-identical to
+    FrontEnd called on the padded float32 batch — including a batch whose longest utterance is shorter than n_max
+    (the graph's static shapes are cut back to the batch's own)."""
+    from telugu_asr_b200.synth import draw_lengths, to_pcm16
+    n_max, B = 48000, 12
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    fe = tasr.FrontEnd(math="tf32")
+    fe.set_weights(weights, cuda_device)
+    pipe = tasr.FrontEndPipeline(fe, B, n_max, cuda_device, pcm16=True, slots=2, graph=graph)
+    batches = []
+    for i, top in enumerate((48000, 30000, 48000)):
+        lens = draw_lengths(B, 1600, top, seed=30 + i)
+        lens[0] = top
+        lens[1] = 399
+        wav, ln = oracle.make_waveforms(lens, seed=30 + i, dist="tilt")
+        batches.append((wav, ln))
+    tickets = []
+    for i, (wav, ln) in enumerate(batches):
+        slot = i % 2
+        pipe.stage(slot, [to_pcm16(wav[b, : ln[b]]) for b in range(B)])
+        tk = pipe.submit(slot)
+        if i == 0:
+            tickets.append(tuple(t.clone() for t in tk.wait()))   # slot 0 is reused by batch 2
+        else:
+            tickets.append(tk)
+    pipe.drain()
+    for i, (wav, ln) in enumerate(batches):
+        got = tickets[i] if i == 0 else tickets[i].wait()
+        want = _call_or_skip(fe, gpu(wav[:, : int(ln.max())], cuda_device), gpu(ln, cuda_device), max_length=int(ln.max()))
+        torch.cuda.synchronize()
+        for g, w in zip(got, want):
+            assert tuple(g.shape) == tuple(w.shape), (i, g.shape, w.shape)
+            assert torch.equal(g, w.cpu()), i
+    if graph:
+        assert pipe.kernels_per_submit and pipe.kernels_per_submit >= 6

@@ -9,7 +9,7 @@ dev = torch.device("cuda:0")
 wav_np, lens_np = bench.make_batch(0, 256)
 fe = tasr.FrontEnd(math="tf32"); fe.set_weights(bench.make_weights(), dev)
 utts = [to_pcm16(wav_np[b, : lens_np[b]]) for b in range(256)]
-pipe = tasr.FrontEndPipeline(fe, 256, wav_np.shape[1], dev, pcm16=True, slots=2)
+pipe = tasr.FrontEndPipeline(fe, 256, wav_np.shape[1], dev, pcm16=True, slots=2, graph=False)
 for s in range(2): pipe.stage(s, utts)
 def run(K=100):
     for i in range(4): tk = pipe.submit(i % 2)
