@@ -1,5 +1,6 @@
-// SeparableConv1D forward, persistent warp-specialised TF32 kernel (sm_100a).  EXPERIMENTAL, opt-in
-// (TASR_SEPCONV_WS=1 at plan creation); the default is the per-tile kernel of sepconv_tf32.cu.
+// SeparableConv1D forward, persistent warp-specialised TF32 kernel (sm_100a).  Default for layers with
+// c_in >= 192 (layers 2 and 3 of the reference stack); TASR_SEPCONV_WS=0 at plan creation selects the per-tile
+// kernel of sepconv_tf32.cu everywhere, =1 this kernel everywhere.
 //
 // Same arithmetic, operand layouts and summation order as sepconv_tf32.cu (its output is bit-identical,
 // tested); what changes is the schedule.  sepconv_tf32_kernel runs one CTA per 128-frame tile and walks
@@ -173,8 +174,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const __grid_
       const int cf = (max(a.len0[u], 0) + (1 << a.shift) - 1) >> a.shift;
       ct = min(wa.n_tiles, (cf + 2 * kMT - 1) / (2 * kMT));      // tiles t0 with 2*t0 < cf
     }
+    int ft = wa.n_tiles - ct;
+    if (a.len0 != nullptr && a.fill_rows >= 0) {   // lean: only padding tiles that start within fill_rows of the data
+      const int cf = (max(a.len0[u], 0) + (1 << a.shift) - 1) >> a.shift;
+      const int lim = ((cf + 1) >> 1) + a.fill_rows;            // tiles with t0 < lim are written
+      ft = max(0, min(wa.n_tiles, (lim + kMT - 1) / kMT) - ct);
+    }
     cum_c[u + 1] = ct * wa.n_split;
-    cum_f[u + 1] = wa.n_tiles - ct;
+    cum_f[u + 1] = ft;
   }
   __syncthreads();
   if (warp == 0) {   // inclusive scans of the two count arrays (B <= 1024: 32 steps of a 32-wide scan)

@@ -526,9 +526,9 @@ def test_featurizer_waveform_mode(cuda_device):
 
 
 def test_sepconv_persistent_kernel_matches_per_tile_kernel_bitwise(cuda_device, monkeypatch):
-    """csrc/sepconv_ws.cu (persistent, warp-specialised; opt-in with TASR_SEPCONV_WS=1) and
-    csrc/sepconv_tf32.cu (one CTA per tile; the default) do the same arithmetic in the same order:
-    identical bits, dense and ragged."""
+    """csrc/sepconv_ws.cu (persistent, warp-specialised; default for c_in >= 192, TASR_SEPCONV_WS=1/0 forces it
+    on/off for every layer) and csrc/sepconv_tf32.cu (one CTA per tile) do the same arithmetic in the same order:
+    identical bits — dense, ragged, and ragged with lean intermediates on NaN-poisoned buffers."""
     from telugu_asr_b200.synth import draw_lengths
     lens = draw_lengths(40, 1600, 240000, seed=13)
     lens[1], lens[2] = 399, 240000
@@ -537,12 +537,22 @@ def test_sepconv_persistent_kernel_matches_per_tile_kernel_bitwise(cuda_device, 
     feat = tasr.SpeechFeaturizer(**tasr.REFERENCE_SPEECH_CONFIG)
     feats, nf = feat(gpu(wav, cuda_device), gpu(ln, cuda_device))
     res = {}
-    for ws in ("1", "0"):
-        monkeypatch.setenv("TASR_SEPCONV_WS", ws)
+    for ws in ("1", "0", None):
+        if ws is None:
+            monkeypatch.delenv("TASR_SEPCONV_WS", raising=False)
+        else:
+            monkeypatch.setenv("TASR_SEPCONV_WS", ws)
         for ragged in (True, False):
             layer = tasr.Conv1DSubsamplingLayer(192, tasr.REFERENCE_SUBSAMPLING_CONFIG, math="tf32", assume_zero_padding=ragged)
             layer.set_weights(weights, cuda_device)
             res[(ws, ragged)] = _call_or_skip(layer, feats, mask=nf)[0]
+            if ragged:
+                _native.poison_allocations = True
+                try:
+                    res[(ws, "lean")] = _call_or_skip(layer, feats, mask=nf, lean_intermediates=True)[0]
+                    torch.cuda.synchronize()
+                finally:
+                    _native.poison_allocations = False
     torch.cuda.synchronize()
     base = res[("0", False)]
     for key, val in res.items():
