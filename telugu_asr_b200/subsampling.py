@@ -68,6 +68,7 @@ class Conv1DSubsamplingLayer:
         self.weights: list[tuple[torch.Tensor, torch.Tensor, torch.Tensor]] | None = None  # per layer (dw, pw, bias)
         self._plans: list[int] | None = None
         self._device = None
+        self._side_streams: dict = {}
 
     # ------------------------------------------------------------------ weights
     def layer_dims(self):
@@ -228,6 +229,37 @@ class Conv1DSubsamplingLayer:
         tasr_sepconv_ragged_margin): what a lean producer has to keep filled."""
         return int(_native.lib().tasr_sepconv_ragged_margin())
 
+    def _lengths_on_side_stream(self, lengths: torch.Tensor, max_frames: int | None):
+        """The lengths + mask kernel enqueued on a per-device side stream that forks from the current stream;
+        returns (len_all, mask, side_stream) — the caller joins with `current.wait_stream(side)`.  Outputs are
+        allocated under the CURRENT stream before the fork (so the caching allocator never sees a cross-stream
+        hand-over).  Without `max_frames` the mask width needs a device->host read, which would stall the fork:
+        that case stays on the current stream, as does stage timing."""
+        if max_frames is None or _native.stage_marks is not None:
+            return None
+        dev = lengths.device
+        n = len(self.kernel_size)
+        B = lengths.numel()
+        width = int(max_frames)
+        for i in range(n):
+            width = get_conv_length(width, self.kernel_size[i], self.padding[i], self.strides[i])
+        width = max(width, 0)
+        lengths = lengths.to(torch.int32).contiguous()
+        len_out = torch.empty((n, B), dtype=torch.int32, device=dev)
+        mask = torch.empty((B, width), dtype=torch.float32, device=dev)
+        k = (C.c_int32 * n)(*self.kernel_size)
+        s = (C.c_int32 * n)(*self.strides)
+        same = (C.c_int32 * n)(*[int(p == "same") for p in self.padding])
+        side = self._side_streams.get(dev)
+        with torch.cuda.device(dev):
+            if side is None:
+                side = self._side_streams[dev] = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            _native.check(_native.lib().tasr_conv_lengths_mask(
+                lengths.data_ptr(), B, n, k, s, same, len_out.data_ptr(), mask.data_ptr() if width else None, width,
+                side.cuda_stream))
+        return len_out, mask, side
+
     def __call__(self, inputs: torch.Tensor, training: bool = False, mask=None, return_lengths: bool = False,
                  max_frames: int | None = None, lean_intermediates: bool = False, input_gain=None):
         """`lean_intermediates` (ragged TF32 path only): the outputs of all layers but the last are not
@@ -267,6 +299,12 @@ class Conv1DSubsamplingLayer:
             else:
                 raise ValueError("mask must be lengths [B], [B,T] or [B,T,F]")
 
+        # lengths + padding mask depend on the frame counts only: they run on a side stream (forked here, joined after
+        # the last layer; inside a CUDA-graph capture this becomes a parallel branch) instead of trailing the stack
+        side_result = None
+        if lengths is not None and B:
+            side_result = self._lengths_on_side_stream(lengths, max_frames)
+
         use_tf32 = self.math == "tf32"
         if input_gain is not None and not (use_tf32 and prefix_lengths and self.assume_zero_padding):
             raise ValueError("input_gain needs the ragged TF32 path: math='tf32', assume_zero_padding=True and mask=n_frames [B]")
@@ -301,7 +339,10 @@ class Conv1DSubsamplingLayer:
                 _native.mark(f"sepconv_layer{i + 1}")
                 h, t_in = y, t_out
         padding_mask, len_all = None, None
-        if lengths is not None:
+        if side_result is not None:
+            len_all, padding_mask, side = side_result
+            torch.cuda.current_stream(x.device).wait_stream(side)
+        elif lengths is not None:
             len_all, padding_mask = self.conv_lengths(lengths, with_mask=True, max_frames=max_frames)
             _native.mark("lengths_mask")
         if return_lengths:
