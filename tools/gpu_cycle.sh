@@ -11,6 +11,6 @@ python tools/time_stages.py > $O/stages_$TAG.log 2>&1; cat $O/stages_$TAG.log
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_$TAG.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu1_$TAG.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k "regex:logmel_kernel|sepconv_tf32|absmax" -s 60 -c 5 -f \
+ncu --set full --clock-control none --import-source on -k "regex:logmel_kernel|sepconv" -s 48 -c 4 -f \
     -o $O/prof_$TAG python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu2_$TAG.log 2>&1
 echo "ncu rc=$?"

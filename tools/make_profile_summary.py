@@ -27,9 +27,10 @@ src = os.path.join(G, f"launches_{tag}.csv")
 shutil.copy(src, os.path.join(P, f"{name}_launches.csv"))
 rows = list(csv.DictReader(l for l in open(src) if l.startswith('"')))
 launches = [(short(r["Kernel Name"]), r["Grid Size"], r["Block Size"], float(r["Metric Value"]) / 1e3) for r in rows]
-# one step = from one absmax launch to the next, taken in the middle of the run (graph replays / the eager stage
+# one step = from one launch of the step's first kernel to the next, taken in the middle of the run (graph replays / the eager stage
 # pass on the real batch; the first launches are plan set-up and the graph-capture warm-ups on empty buffers)
-idx = [i for i, l in enumerate(launches) if l[0] == "absmax_kernel"]
+first = "absmax_kernel" if any(l[0] == "absmax_kernel" for l in launches) else "logmel_kernel<1>"   # two-pass / single-pass step
+idx = [i for i, l in enumerate(launches) if l[0] == first]
 mid = len(idx) // 2
 step = [l for l in launches[idx[mid]:idx[mid + 1]] if not l[0].startswith("at::")]
 total = sum(l[3] for l in step)
@@ -85,8 +86,8 @@ with open(os.path.join(P, f"{name}_summary.md"), "w") as fh:
     fh.write("Commands (1 x B200 under `gpurun`, `tools/gpu_cycle.sh`): `python bench.py` (plain, the bench line below), then\n"
              "`python bench.py --steps 3 --warmup 3 --no-cpu-baseline` plain (exit 0) and the same under\n"
              "`ncu --metrics gpu__time_duration.sum --clock-control none` (launch list) and\n"
-             "`ncu --set full --clock-control none --import-source on -k regex:logmel_kernel|sepconv_tf32|absmax -s 60 -c 5`\n"
-             "(five consecutive kernels of the eager stage-timing pass on the bench batch).  ncu per-launch times are cold-cache and serialised: compare shares.\n\n")
+             "`ncu --set full --clock-control none --import-source on -k regex:logmel_kernel|sepconv -s 48 -c 4`\n"
+             "(four consecutive kernels of the eager stage-timing pass on the bench batch).  ncu per-launch times are cold-cache and serialised: compare shares.\n\n")
     fh.write(f"Bench line (not under ncu): **{bj['value']:.0f} audio-s/s**, {bj['ms_per_step'] * 1e3:.1f} us/step; "
              f"e2e {bj['e2e']['value']:.0f} audio-s/s ({bj['e2e']['ms_per_step']:.3f} ms/step, H2D {bj['e2e']['h2d_bytes_per_step'] / 1e6:.1f} MB, "
              f"D2H {bj['e2e']['d2h_bytes_per_step'] / 1e6:.1f} MB); roofline {bj['roofline']['kernel']} "
