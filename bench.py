@@ -504,7 +504,7 @@ def main():
             "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "audio_seconds_per_step_per_gpu": audio_s,
                        "distribution": "AR(1) rho=0.97 'tilt', peak 0.5, k/32768, seeds 2+rank",
                        "pointwise_math": math_mode + (" (tcgen05 kind::tf32, fp32 accumulate)" if math_mode == "tf32" else " (CUDA-core FMA)"),
-                       "l2": "inputs larger than L2: 246 MB padded waveforms + 123 MB features + 350 MB activations per step vs 126 MB L2; no flush needed",
+                       "l2": "inputs larger than L2: 246 MB padded waveforms (128 MB of samples read) per step and two steps in flight vs 126 MB L2; no flush needed",
                        "parallelism": f"dp{world} by utterance, no data-path collective",
                        "intermediates": ("lean: the log-mel tensor and the activations of layers 1-2 are not written far inside the "
                                          "collate padding (no kernel reads them there); encoder input, mask and lengths are bit-identical "
@@ -519,13 +519,13 @@ def main():
                          "kernel_share_of_step": k_ms / (ms_total / args.steps),
                          "ncu": ({"source": tj.get("source"), **{kk: ncu_lm.get(kk) for kk in ("dram_pct", "issue_active_pct", "fma_pipe_pct", "warp_instructions", "registers", "warps_active_pct")}}
                                  if ncu_lm else None),
-                         "note": "HBM is the contract bound (SURVEY.md 8d); the kernel is latency-bound at 16 resident warps/SM (61 % issue, 39 % FMA pipe, 18 % DRAM in ncu; an FP32x2 variant with 31 % fewer instructions takes the same time), see DESIGN.md 4.2; kernel_ms is its single-stream time, the step overlaps two batches"},
+                         "note": "HBM is the contract bound (SURVEY.md 8d: the waveform read once, the features written once — the kernel now does exactly that, it finds max|x| itself); it is latency-bound at 16 resident warps/SM (issue / FMA-pipe / DRAM utilisation in roofline.ncu; variants with 31 % fewer instructions or with the global loads hidden take the same time or longer), see DESIGN.md 4.2; kernel_ms is its single-stream time, the step overlaps two batches"},
             "e2e": {"value": e2e_val, "unit": "audio-seconds/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps, "gpu_launches": e2e_launches,
                     "matches_device_resident_result": e2e_ok, "windows": e2e_windows,
                     "pcie_h2d_gbs": h2d / (e2e_ms_max / e2e_steps * 1e-3) / 1e9,
                     "api": "telugu_asr_b200.FrontEndPipeline.submit: ragged int16 PCM in pinned host memory (valid samples only) -> "
-                           "H2D -> unpack -> peak -> log-mel -> 3x sepconv -> lengths/mask -> D2H of [B,T3,192] f32 + mask + len3; "
+                           "H2D -> unpack -> log-mel (single pass) -> 3x sepconv -> lengths/mask -> D2H of [B,T3,192] f32 + mask + len3; "
                            "three streams, double-buffered slots; the device side of a submit (unpack, front end, D2H) is one "
                            "CUDA-graph launch per slot",
                     "f32_padded_single_stream": {"value": audio_s / (pad_ms * 1e-3), "ms_per_step": pad_ms,
