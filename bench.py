@@ -516,7 +516,11 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "logmel_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
-                         "kernel_share_of_step": k_ms / (ms_total / args.steps),
+                         # share of the step's kernel time (sum of the single-stream stage times: comparable with the ncu
+                         # launch list, which serialises the kernels); the timed step overlaps two batches, so kernel_ms
+                         # divided by ms_per_step would overstate it
+                         "kernel_share_of_step": (k_ms * 1e3) / max(sum(stage_us.values()), 1e-9),
+                         "kernel_ms_over_ms_per_step": k_ms / (ms_total / args.steps),
                          "ncu": ({"source": tj.get("source"), **{kk: ncu_lm.get(kk) for kk in ("dram_pct", "issue_active_pct", "fma_pipe_pct", "warp_instructions", "registers", "warps_active_pct")}}
                                  if ncu_lm else None),
                          "note": "HBM is the contract bound (SURVEY.md 8d: the waveform read once, the features written once — the kernel now does exactly that, it finds max|x| itself); it is latency-bound at 16 resident warps/SM (issue / FMA-pipe / DRAM utilisation in roofline.ncu; variants with 31 % fewer instructions or with the global loads hidden take the same time or longer), see DESIGN.md 4.2; kernel_ms is its single-stream time, the step overlaps two batches"},
