@@ -1,0 +1,518 @@
+// EXPERIMENT (not built): sepconv_ws.cu with the two N-slices of layer 2 fed from ONE depthwise pass per tile (work items are
+// tiles; chunk-major MMAs into two TMEM slots; 3-deep B ring, 2-deep x ring).  Bit-identical (GPU tests pass) and SLOWER:
+// layer 2 96 vs 80 us on config 3.  Both accumulator slots then belong to one tile, so consecutive tiles no longer
+// double-buffer: the epilogue (384 columns, ~7 us on its eight warps) and the next main loop serialise.  Halving the
+// depthwise work does not pay while the epilogue is the longer half; it would need 768 TMEM columns or a faster epilogue.
+// SeparableConv1D forward, persistent warp-specialised TF32 kernel (sm_100a).  Default for layers with
+// c_in >= 192 (layers 2 and 3 of the reference stack); TASR_SEPCONV_WS=0 at plan creation selects the per-tile
+// kernel of sepconv_tf32.cu everywhere, =1 this kernel everywhere.
+//
+// Same arithmetic, operand layouts and summation order as sepconv_tf32.cu (its output is bit-identical,
+// tested); what changes is the schedule.  sepconv_tf32_kernel runs one CTA per 128-frame tile and walks
+// its channel chunks in lock step (depthwise -> barrier -> MMA issue).  Here ONE CTA per SM lives for the
+// whole layer and its warps take roles:
+//
+//   warp 17     x loader: TMA tiled loads (cp.async.bulk.tensor.3d, tensor map over (C_in, T_in, B)) of each
+//               (tile, chunk) input window — 264 rows x 32 channels, out-of-range rows/channels zero-filled by
+//               the hardware — into a 3-deep shared ring, two chunks ahead of the arithmetic;
+//   warps 0-7   depthwise producers: lane <-> channel, a run of 16 output frames per warp from rows
+//               [32w, 32w+39) of the staged window (conflict-free 128-byte rows), result rounded to TF32 into
+//               a 2-deep A ring (UMMA K-major SWIZZLE_128B), mbarrier hand-off per stage — no CTA-wide barrier;
+//   warp 16     B loader: cp.async.bulk (TMA bulk copy) of the packed pw^T chunk into a 2-deep B ring;
+//   warp 18     MMA issuer: tcgen05.mma kind::tf32, M=128, N=NT, accumulators double-buffered in TMEM
+//               (2 x NT columns of the 512), tcgen05.commit frees ring stages and publishes accumulators;
+//   warps 8-15  epilogue: tcgen05.ld -> +bias -> activation (SFU) -> per-warp transpose in shared memory ->
+//               128-bit coalesced stores, overlapped with the next tile's main loop; they also write the
+//               constant padding rows of the ragged mode (tiles that lie entirely in the collate padding).
+//
+// Work distribution: the tiles that need computing are enumerated through a block-wide prefix sum over the
+// utterances (ragged: ceil(cf/256) tiles per utterance, cf = ceil(n_frames / 2^layer)) and dealt round-robin
+// to the CTAs, so every SM gets the same number +-1; the padding tiles are dealt the same way.
+//
+// Status (round 1, B200, config 3): 62 / 82 / 63 us for the three layers against 62 / 94 / 68 us for the
+// per-tile kernel inside a step (369 vs 387 us per step on one stream; with two steps in flight on two
+// streams the difference shrinks to 347 vs 351 us, which is why it is not the default yet).  A globaltimer
+// trace of CTA 0 (tools/ws_trace.py) shows what paces it: a 32-channel chunk takes ~1.05 us in the depthwise
+// warps — ~0.2 us fetching the taps, ~0.1 us barrier wake-up, ~0.4 us window -> registers + hand-off,
+// ~0.45 us FMAs + TF32 store + proxy fence — all serial latency in two warps per scheduler, and a tile's
+// epilogue takes 6-9 us on its eight warps.  Earlier variants (per-lane LDG windows, cp.async windows,
+// 16 depthwise warps, K=64 per stage, deeper B ring) all landed within 5 % of the per-tile kernel.
+#include "sepconv_common.cuh"
+#include <cuda.h>
+
+using namespace tasr;
+using namespace tasr_sep;
+
+namespace {
+
+constexpr int kDwWarps = 8;
+constexpr int kRunWs = kMT / kDwWarps;          // 16 output frames per depthwise warp
+constexpr int kWinWs = 2 * (kRunWs - 1) + 9;    // 39 input rows per run
+constexpr int kEpWarps = 8;
+constexpr int kWsThreads = (kDwWarps + kEpWarps + 3) * 32;   // 608: + B loader, x loader, MMA issuer
+constexpr int kStagesA = 2;   // depthwise -> MMA ring (16 KB each)
+constexpr int kMaxStagesB = 4; // pw^T chunk ring (NT*128 B each): 2 stages for one N-slice per tile, 3 for two
+constexpr int kMaxStagesX = 4; // input-tile ring (264 rows x 32 channels fetched by TMA ahead of the arithmetic): 3 / 2
+__host__ __device__ inline int ws_stages_b(int n_split) { return n_split >= 2 ? 3 : 2; }
+__host__ __device__ inline int ws_stages_x(int n_split) { return n_split >= 2 ? 2 : 3; }
+constexpr int kXRows = 264;   // 2*(128-1)+9 = 263 rows per 128-frame tile, fetched as boxes of 256 + 8 rows
+constexpr int kXBytes = kXRows * kKC * 4;
+constexpr int kMaxUtt = 512;      // utterances indexed in shared memory
+constexpr int kListCap = 256;    // work items per CTA
+constexpr int kTmemColsWs = 512;
+
+// TMA tiled load of a 3-D box (coordinates: channel, row, utterance) onto an mbarrier; out-of-range rows and
+// channels arrive as zeros.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+struct WsLayout {
+  uint32_t a, b, xs, stg, bias, cum_c, cum_f, list_c, list_cf, list_f, bars, tmem_slot, total;
+};
+__host__ __device__ inline WsLayout ws_layout(int NT, int C_out, int n_split) {
+  WsLayout L;
+  uint32_t o = 0;
+  L.a = o; o += kStagesA * kABytes;
+  L.b = o; o += (uint32_t)ws_stages_b(n_split) * (uint32_t)NT * 128u;
+  L.xs = o; o += (uint32_t)ws_stages_x(n_split) * kXBytes;
+  L.stg = o; o += kEpWarps * 32 * kStgStride * 4;
+  L.bias = o; o += (uint32_t)((C_out + 3) & ~3) * 4u;
+  L.cum_c = o; o += (kMaxUtt + 1) * 4;
+  L.cum_f = o; o += (kMaxUtt + 1) * 4;
+  L.list_c = o; o += kListCap * 4;
+  L.list_cf = o; o += kListCap * 4;
+  L.list_f = o; o += kListCap * 4;
+  o = (o + 7u) & ~7u;
+  L.bars = o; o += 32 * 8;
+  L.tmem_slot = o; o += 16;
+  L.total = o;
+  return L;
+}
+
+struct WsArgs {
+  CUtensorMap tm_hi;   // x as (C_in, T_in, B) float32, box 32 channels x 256 rows
+  CUtensorMap tm_lo;   // same tensor, box 32 channels x 8 rows (rows 256..263 of a tile's window)
+  SepArgs s;
+  int32_t B, n_tiles, n_split;
+  long long* trace;   // development aid (tools/ws_trace.py): per-role (tag, globaltimer) log of CTA 0, or null
+};
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define WS_TRACE(role, tag)                                                            \
+  do {                                                                                 \
+    if (wa.trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_n < 250) {        \
+      wa.trace[(role) * 512 + 2 * trace_n] = (tag);                                    \
+      wa.trace[(role) * 512 + 2 * trace_n + 1] = gtime();                              \
+      ++trace_n;                                                                       \
+    }                                                                                  \
+  } while (0)
+
+template <int CIN, int ACT>
+__global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const __grid_constant__ WsArgs wa) {
+  const SepArgs& a = wa.s;
+  const int C_in = CIN ? CIN : a.C_in;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  unsigned char* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NT = a.NT;
+  const uint32_t bBytes = (uint32_t)NT * 128u;
+  const WsLayout L = ws_layout(NT, a.C_out, wa.n_split);
+  const int S = wa.n_split;                 // N-slices per tile: they share ONE depthwise pass (S <= 2)
+  const int kStagesB = ws_stages_b(S), kStagesX = ws_stages_x(S);
+  const long long t_entry = (wa.trace != nullptr) ? gtime() : 0;
+
+  unsigned char* sA = sm + L.a;
+  float* sBias = reinterpret_cast<float*>(sm + L.bias);
+  int32_t* cum_c = reinterpret_cast<int32_t*>(sm + L.cum_c);
+  int32_t* cum_f = reinterpret_cast<int32_t*>(sm + L.cum_f);
+  int32_t* list_c = reinterpret_cast<int32_t*>(sm + L.list_c);
+  int32_t* list_cf = reinterpret_cast<int32_t*>(sm + L.list_cf);   // cf of each compute item (rows 2t >= cf are padding)
+  int32_t* list_f = reinterpret_cast<int32_t*>(sm + L.list_f);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem_slot);
+  const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sm + L.b), bar_u = smem_u32(sm + L.bars);
+  // barriers: A full (one arrival per depthwise warp) / A empty (commit), B full (tx) / B empty (commit),
+  //           accumulator full (commit) / accumulator empty (one arrival per epilogue warp)
+  auto bar_afull = [&](int s) { return bar_u + 8u * (uint32_t)s; };
+  auto bar_aempty = [&](int s) { return bar_u + 8u * (uint32_t)(kStagesA + s); };
+  auto bar_bfull = [&](int s) { return bar_u + 8u * (uint32_t)(2 * kStagesA + s); };
+  auto bar_bempty = [&](int s) { return bar_u + 8u * (uint32_t)(2 * kStagesA + kMaxStagesB + s); };
+  auto bar_accf = [&](int i) { return bar_u + 8u * (uint32_t)(2 * kStagesA + 2 * kMaxStagesB + i); };
+  auto bar_acce = [&](int i) { return bar_u + 8u * (uint32_t)(2 * kStagesA + 2 * kMaxStagesB + 2 + i); };
+  auto bar_xfull = [&](int s) { return bar_u + 8u * (uint32_t)(2 * kStagesA + 2 * kMaxStagesB + 4 + s); };
+  auto bar_xempty = [&](int s) { return bar_u + 8u * (uint32_t)(2 * kStagesA + 2 * kMaxStagesB + 4 + kMaxStagesX + s); };
+  const uint32_t sX_u = smem_u32(sm + L.xs);
+  constexpr int kWarpB = kDwWarps + kEpWarps, kWarpX = kWarpB + 1, kWarpMma = kWarpB + 2;
+
+  // ---- prologue: TMEM, barriers, bias, work lists ---------------------------------------------------
+  if (warp == kWarpMma) tmem_alloc(smem_u32(tmem_slot), kTmemColsWs);
+  if (tid == 0) {
+    for (int s = 0; s < kStagesA; ++s) {
+      mbar_init(bar_afull(s), kDwWarps);
+      mbar_init(bar_aempty(s), 1);
+    }
+    for (int s = 0; s < kStagesB; ++s) {
+      mbar_init(bar_bfull(s), 1);
+      mbar_init(bar_bempty(s), 1);
+    }
+    for (int s = 0; s < kStagesX; ++s) {
+      mbar_init(bar_xfull(s), 1);
+      mbar_init(bar_xempty(s), kDwWarps);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_accf(i), 1);
+      mbar_init(bar_acce(i), kEpWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < a.C_out; i += kWsThreads) sBias[i] = a.bias[i];
+  // per utterance: tiles that must be computed (receptive field reaches real data) and tiles that are padding
+  for (int u = tid; u < wa.B; u += kWsThreads) {
+    int ct = wa.n_tiles;
+    if (a.len0 != nullptr) {
+      const int cf = (max(a.len0[u], 0) + (1 << a.shift) - 1) >> a.shift;
+      ct = min(wa.n_tiles, (cf + 2 * kMT - 1) / (2 * kMT));      // tiles t0 with 2*t0 < cf
+    }
+    int ft = wa.n_tiles - ct;
+    if (a.len0 != nullptr && a.fill_rows >= 0) {   // lean: only padding tiles that start within fill_rows of the data
+      const int cf = (max(a.len0[u], 0) + (1 << a.shift) - 1) >> a.shift;
+      const int lim = ((cf + 1) >> 1) + a.fill_rows;            // tiles with t0 < lim are written
+      ft = max(0, min(wa.n_tiles, (lim + kMT - 1) / kMT) - ct);
+    }
+    cum_c[u + 1] = ct;
+    cum_f[u + 1] = ft;
+  }
+  __syncthreads();
+  if (warp == 0) {   // inclusive scans of the two count arrays (B <= 1024: 32 steps of a 32-wide scan)
+    int carry_c = 0, carry_f = 0;
+    for (int base = 0; base < wa.B; base += 32) {
+      const int u = base + lane;
+      int vc = (u < wa.B) ? cum_c[u + 1] : 0, vf = (u < wa.B) ? cum_f[u + 1] : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int c2 = __shfl_up_sync(0xffffffffu, vc, d), f2 = __shfl_up_sync(0xffffffffu, vf, d);
+        if (lane >= d) { vc += c2; vf += f2; }
+      }
+      if (u < wa.B) { cum_c[u + 1] = carry_c + vc; cum_f[u + 1] = carry_f + vf; }
+      carry_c += __shfl_sync(0xffffffffu, vc, 31);
+      carry_f += __shfl_sync(0xffffffffu, vf, 31);
+    }
+    if (lane == 0) { cum_c[0] = 0; cum_f[0] = 0; }
+  }
+  __syncthreads();
+  const int total_c = cum_c[wa.B], total_f = cum_f[wa.B];
+  const int G = (int)gridDim.x, me = (int)blockIdx.x;
+  const int n_c = (total_c > me) ? (total_c - me - 1) / G + 1 : 0;   // <= kListCap (checked by the host)
+  const int n_f = (total_f > me) ? (total_f - me - 1) / G + 1 : 0;
+  auto find = [&](const int32_t* cum, int x) -> int {   // largest u in [0,B) with cum[u] <= x
+    int lo = 0, hi = wa.B;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (cum[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+  };
+  for (int k = tid; k < n_c; k += kWsThreads) {
+    const int j = me + k * G;
+    const int u = find(cum_c, j);
+    const int tile = j - cum_c[u];
+    list_c[k] = (u << 16) | (tile << 4);
+    list_cf[k] = (a.len0 != nullptr) ? ((max(a.len0[u], 0) + (1 << a.shift) - 1) >> a.shift) : 0x7fffffff;
+  }
+  for (int k = tid; k < n_f; k += kWsThreads) {
+    const int j = me + k * G;
+    const int u = find(cum_f, j);
+    const int ct = cum_c[u + 1] - cum_c[u];
+    list_f[k] = (u << 16) | (ct + (j - cum_f[u]));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (wa.trace != nullptr && blockIdx.x == 0 && tid == 0) { wa.trace[5 * 512] = 1; wa.trace[5 * 512 + 1] = gtime(); wa.trace[5 * 512 + 2] = n_c; wa.trace[5 * 512 + 3] = n_f; wa.trace[5 * 512 + 4] = t_entry; }
+  const uint32_t tmem = *tmem_slot;
+  const int n_chunks = a.n_chunks;
+  int trace_n = 0;
+
+  if (warp < kDwWarps) {
+    // =========================== depthwise producers ===========================================
+    // The input window of every (tile, chunk) — 264 rows x 32 channels — is brought into the shared x ring by
+    // the TMA warp two chunks ahead; each warp reduces its run of 16 output frames from rows [32w, 32w+39)
+    // of it (lane <-> channel, conflict-free rows of 128 B) into the A ring.
+    const float* xs_f = reinterpret_cast<const float*>(sm + L.xs);
+    auto load_w = [&](float (&w)[9], int kc) {     // depthwise taps of chunk kc for this lane's channel
+      const int c0 = kc * kKC;
+      const bool cok = lane < min(kKC, C_in - c0);
+#pragma unroll
+      for (int kk = 0; kk < 9; ++kk) w[kk] = cok ? __ldg(a.dw + kk * C_in + c0 + lane) : 0.0f;
+    };
+    float w[9], wn[9];
+    if (n_c > 0) load_w(w, 0);
+    int g = 0;
+    for (int k = 0; k < n_c; ++k) {
+      const int r0 = 2 * (((list_c[k] >> 4) & 0xfff) * kMT + warp * kRunWs);   // first input row of this warp's run
+      const bool run_needed = (r0 < list_cf[k]);   // a run that starts in the padding only yields the constant row
+      for (int kc = 0; kc < n_chunks; ++kc, ++g) {
+        load_w(wn, (kc + 1 < n_chunks) ? kc + 1 : 0);           // next chunk's taps: one chunk of latency hiding
+        const int sx = g % kStagesX, nx = g / kStagesX;
+        const int s = g % kStagesA, n = g / kStagesA;
+        if (warp == 0) WS_TRACE(0, 140 + kc);
+        mbar_wait(bar_xfull(sx), nx & 1);
+        if (warp == 0) WS_TRACE(0, 160 + kc);
+        float v[kWinWs];
+        if (run_needed) {
+          const float* xw = xs_f + (size_t)sx * (kXBytes / 4) + (size_t)(2 * warp * kRunWs) * kKC + lane;
+#pragma unroll
+          for (int i = 0; i < kWinWs; ++i) v[i] = xw[i * kKC];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_xempty(sx));            // this warp has its window in registers
+        if (n > 0) mbar_wait(bar_aempty(s), (n - 1) & 1);
+        if (warp == 0) WS_TRACE(0, 100 + kc);
+        if (run_needed) {
+          unsigned char* As = sA + s * kABytes;
+#pragma unroll
+          for (int j = 0; j < kRunWs; ++j) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int kk = 0; kk < 9; ++kk) acc = fmaf(v[2 * j + kk], w[kk], acc);
+            const int row = warp * kRunWs + j;
+            const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u;
+            *reinterpret_cast<uint32_t*>(As + off) = to_tf32(acc);
+          }
+        }
+        fence_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_afull(s));
+        if (warp == 0) WS_TRACE(0, 200 + kc);
+#pragma unroll
+        for (int kk = 0; kk < 9; ++kk) w[kk] = wn[kk];
+      }
+    }
+  } else if (warp < kDwWarps + kEpWarps) {
+    // =========================== epilogue + padding fill ========================================
+    const int e = warp - kDwWarps;
+    const int q = e & 3, half = e >> 2;      // TMEM lane quadrant (= warp id % 4), column-group parity
+    float* stg = reinterpret_cast<float*>(sm + L.stg) + e * (32 * kStgStride);
+    const int ngroups = NT >> 5;
+    const int q4 = a.C_out >> 2;
+    int fdone = 0;
+    auto do_fill = [&](int upto) {           // padding tiles: whole rows of the constant padding row
+      for (; fdone < upto; ++fdone) {
+        const int item = list_f[fdone];
+        const int b = item >> 16, t0 = (item & 0xffff) * kMT;
+        const int rows = min(kMT, a.T_out - t0);
+        float* dst = a.y + ((size_t)b * a.T_out + t0) * a.C_out;
+        const float4* pr = reinterpret_cast<const float4*>(a.pad_out);
+        for (int c4 = lane; c4 < q4; c4 += 32) {
+          const float4 pv = __ldg(pr + c4);
+          for (int r = e; r < rows; r += kEpWarps) *reinterpret_cast<float4*>(dst + (size_t)r * a.C_out + 4 * c4) = pv;
+        }
+      }
+    };
+    for (int k = 0; k < n_c; ++k) {
+      const int item = list_c[k];
+      const int b = item >> 16, t0 = ((item >> 4) & 0xfff) * kMT;
+      const int cf = list_cf[k];
+      for (int nh = 0; nh < S; ++nh) {
+      const int n0 = nh * NT;
+      const int qi = k * S + nh;               // running slice index: accumulator slot qi & 1
+      const int acc = qi & 1;
+      if (e == 0 || e == 7) WS_TRACE(e == 0 ? 3 : 4, 300);
+      mbar_wait(bar_accf(acc), (qi >> 1) & 1);
+      tc_fence_after();
+      if (e == 0 || e == 7) WS_TRACE(e == 0 ? 3 : 4, 301);
+      for (int g = half; g < ngroups; g += 2) {
+        uint32_t r[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + g * 32), r);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bv = *reinterpret_cast<const float4*>(sBias + n0 + g * 32 + 4 * i);
+          float4 o;
+          o.x = act_apply<ACT>(__uint_as_float(r[4 * i + 0]) + bv.x);
+          o.y = act_apply<ACT>(__uint_as_float(r[4 * i + 1]) + bv.y);
+          o.z = act_apply<ACT>(__uint_as_float(r[4 * i + 2]) + bv.z);
+          o.w = act_apply<ACT>(__uint_as_float(r[4 * i + 3]) + bv.w);
+          *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * i) = o;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = (lane >> 3) + 4 * i;
+          const int c4 = (lane & 7) * 4;
+          float4 o = *reinterpret_cast<const float4*>(stg + rr * kStgStride + c4);
+          const int t = t0 + q * 32 + rr;
+          if (2 * t >= cf) o = __ldg(reinterpret_cast<const float4*>(a.pad_out + n0 + g * 32 + c4));
+          if (t < a.T_out)
+            *reinterpret_cast<float4*>(a.y + ((size_t)b * a.T_out + t) * a.C_out + n0 + g * 32 + c4) = o;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce(acc));   // this warp has read its part of the accumulator
+      if (e == 0 || e == 7) WS_TRACE(e == 0 ? 3 : 4, 302);
+      }
+      do_fill((int)(((long long)n_f * (k + 1)) / n_c));
+      if (e == 0 || e == 7) WS_TRACE(e == 0 ? 3 : 4, 303);
+    }
+    do_fill(n_f);
+    if (e == 0 || e == 7) WS_TRACE(e == 0 ? 3 : 4, 304);
+  } else if (warp == kWarpB) {
+    // =========================== B loader ========================================================
+    if (lane == 0) {
+      int g = 0;
+      for (int k = 0; k < n_c; ++k) {
+        for (int kc = 0; kc < n_chunks; ++kc) {
+          for (int nh = 0; nh < S; ++nh, ++g) {          // chunk-major: both slices' pw^T chunk for one A stage
+            const float* bsrc = a.bpack + ((size_t)nh * n_chunks + kc) * NT * kKC;
+            const int s = g % kStagesB, n = g / kStagesB;
+            if (n > 0) mbar_wait(bar_bempty(s), (n - 1) & 1);
+            mbar_expect_tx(bar_bfull(s), bBytes);
+            bulk_g2s(sB_u + s * bBytes, bsrc, bBytes, bar_bfull(s));
+          }
+        }
+      }
+    }
+  } else if (warp == kWarpX) {
+    // =========================== x loader (TMA) ==================================================
+    if (lane == 0) {
+      int g = 0;
+      for (int k = 0; k < n_c; ++k) {
+        const int item = list_c[k];
+        const int b = item >> 16, row0 = 2 * ((item >> 4) & 0xfff) * kMT;
+        for (int kc = 0; kc < n_chunks; ++kc, ++g) {
+          const int s = g % kStagesX, n = g / kStagesX;
+          if (n > 0) mbar_wait(bar_xempty(s), (n - 1) & 1);
+          WS_TRACE(1, 800 + kc);
+          mbar_expect_tx(bar_xfull(s), (uint32_t)kXBytes);
+          const uint32_t dst = sX_u + (uint32_t)s * kXBytes;
+          tma_load_3d(dst, &wa.tm_hi, kc * kKC, row0, b, bar_xfull(s));
+          tma_load_3d(dst + 256u * kKC * 4u, &wa.tm_lo, kc * kKC, row0 + 256, b, bar_xfull(s));
+        }
+      }
+    }
+  } else {
+    // =========================== MMA issuer ======================================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(kMT, NT);
+      int g = 0, gb = 0;
+      for (int k = 0; k < n_c; ++k) {
+        // The S slices of a tile accumulate side by side (slot = running slice index & 1) from the SAME A stages:
+        // the depthwise result is computed once per tile.  S = 1: the two slots double-buffer consecutive tiles.
+        for (int nh = 0; nh < S; ++nh) {
+          const int qi = k * S + nh;
+          if (qi >= 2) {                     // the epilogue has drained this slot (slice qi-2)
+            mbar_wait(bar_acce(qi & 1), ((qi >> 1) - 1) & 1);
+            tc_fence_after();
+          }
+        }
+        for (int kc = 0; kc < n_chunks; ++kc, ++g) {
+          const int sa = g % kStagesA, na = g / kStagesA;
+          mbar_wait(bar_afull(sa), na & 1);
+          WS_TRACE(2, 400 + kc);
+          const uint64_t da = umma_desc_sw128(sA_u + sa * kABytes);
+          const int ksteps = min(kKC, C_in - kc * kKC) >> 3;
+          for (int nh = 0; nh < S; ++nh, ++gb) {
+            const int sb = gb % kStagesB, nb = gb / kStagesB;
+            mbar_wait(bar_bfull(sb), nb & 1);
+            tc_fence_after();
+            WS_TRACE(2, 500 + kc);
+            const uint32_t d_tmem = tmem + (uint32_t)(((k * S + nh) & 1) * NT);
+            const uint64_t db = umma_desc_sw128(sB_u + sb * bBytes);
+            for (int kk = 0; kk < ksteps; ++kk)
+              umma_tf32(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc, (kc | kk) != 0 ? 1u : 0u);
+            umma_commit(bar_bempty(sb));
+          }
+          umma_commit(bar_aempty(sa));
+        }
+        for (int nh = 0; nh < S; ++nh) umma_commit(bar_accf((k * S + nh) & 1));
+        WS_TRACE(2, 600);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wa.trace != nullptr && blockIdx.x == 0 && tid == 0) wa.trace[5 * 512 + 5] = gtime();
+  if (warp == kWarpMma) tmem_dealloc(tmem, kTmemColsWs);
+}
+
+typedef void (*WsKernel)(const WsArgs);
+template <int CIN>
+WsKernel pick_act_ws(int act) {
+  switch (act) {
+    case TASR_ACT_TANH: return sepconv_ws_kernel<CIN, TASR_ACT_TANH>;
+    case TASR_ACT_GELU_ERF: return sepconv_ws_kernel<CIN, TASR_ACT_GELU_ERF>;
+    case TASR_ACT_RELU: return sepconv_ws_kernel<CIN, TASR_ACT_RELU>;
+    default: return sepconv_ws_kernel<CIN, TASR_ACT_NONE>;
+  }
+}
+WsKernel pick_kernel_ws(int c_in, int act) {
+  switch (c_in) {
+    case 80: return pick_act_ws<80>(act);
+    case 192: return pick_act_ws<192>(act);
+    case 384: return pick_act_ws<384>(act);
+    default: return pick_act_ws<0>(act);
+  }
+}
+
+}  // namespace
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static long long* g_ws_trace = nullptr;
+// Development aid: a device buffer of 6*512 int64 that CTA 0 of the next launches logs (tag, ns) pairs into.
+extern "C" void tasr_debug_ws_trace(long long* dev_buf) { g_ws_trace = dev_buf; }
+
+// Returns TASR_OK after launching, or a negative value when this shape is not handled by the persistent
+// kernel (the caller then uses sepconv_tf32_kernel).
+int tasr_sepconv_ws_launch(const TasrSepConvPlan* p, const SepArgs& sa, int32_t B, cudaStream_t st) {
+  const int n_tiles = (sa.T_out + kMT - 1) / kMT;
+  if (B > kMaxUtt || n_tiles > 0xfff || p->n_split > 2 || 2 * p->NT > kTmemColsWs) return -1;
+  const int grid = sm_count();
+  const long long dense = (long long)B * n_tiles;   // work items are tiles; the n_split slices of a tile share its depthwise pass
+  if ((dense + grid - 1) / grid > kListCap) return -1;
+  const WsLayout L = ws_layout(p->NT, p->L.c_out, p->n_split);
+  const size_t smem = (size_t)L.total + 1024;
+  if (smem > 227 * 1024) return -1;
+  WsKernel kern = pick_kernel_ws(p->L.c_in, p->L.activation);
+  TASR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  WsArgs wa;
+  {
+    static PFN_encodeTiled encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      TASR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      if (!fn || qres != cudaDriverEntryPointSuccess) return -1;
+      encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)p->L.c_in, (cuuint64_t)sa.T_in, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)p->L.c_in * 4, (cuuint64_t)sa.T_in * p->L.c_in * 4};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t box_hi[3] = {(cuuint32_t)kKC, 256, 1}, box_lo[3] = {(cuuint32_t)kKC, 8, 1};
+    CUresult r1 = encode(&wa.tm_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(sa.x), dims, strides, box_hi, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = encode(&wa.tm_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(sa.x), dims, strides, box_lo, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return -1;   // e.g. strides not multiples of 16 bytes: per-tile kernel instead
+  }
+  wa.s = sa; wa.B = B; wa.n_tiles = n_tiles; wa.n_split = p->n_split;
+  wa.trace = g_ws_trace;
+  const int g = (int)(dense < grid ? (dense > 0 ? dense : 1) : grid);
+  kern<<<g, kWsThreads, smem, st>>>(wa);
+  TASR_LAUNCH_CHECK("sepconv_ws_kernel");
+  return TASR_OK;
+}
