@@ -178,3 +178,33 @@ def test_other_feature_types_shapes():
     np.testing.assert_allclose(ln, l10 * np.log(10.0), rtol=1e-5, atol=1e-5)
     pe = featurize_ref(x, FeatParams(pad_end=True, normalize_signal=True), np.float32)
     assert pe.shape == (25, 80)
+
+
+def test_logmel_oracle_vs_transformers_audio_utils():
+    """Independent third-party pin of the whole log-mel chain: `transformers.audio_utils` (numpy; written to reproduce
+    the TF / Kaldi front ends — `triangularize_in_mel_space=True` is its switch for tf.signal.linear_to_mel_weight_matrix)
+    with center=False frames, a periodic Hann window, the frame zero-padded at the TAIL to 512, power spectrum, HTK
+    triangles, log10 with a 1e-9 floor.  Same support of the mel matrix (502 non-zeros, same places), weights within
+    1e-5 (TF builds the matrix in float32, HF in float64), log-mel within 5e-5 end to end and within 5e-6 when HF's
+    chain is handed the oracle's float32-built matrix.  (Normalisation and pre-emphasis are applied to the signal
+    first, as src/speech_featurizer.py:68-79 does; HF's own per-frame Kaldi pre-emphasis is a different operation.)"""
+    au = pytest.importorskip("transformers.audio_utils")
+    from oracle import featurizer_ref as fr
+    W = fr.htk_mel_matrix_f32()
+    fb = au.mel_filter_bank(num_frequency_bins=257, num_mel_filters=80, min_frequency=0.0, max_frequency=8000.0,
+                            sampling_rate=16000, norm=None, mel_scale="htk", triangularize_in_mel_space=True)
+    assert fb.shape == W.shape == (257, 80)
+    assert np.array_equal(W != 0, fb > 1e-12) and int((W != 0).sum()) == 502
+    assert np.abs(W - fb).max() <= 1e-5
+    win = au.window_function(400, "hann", periodic=True)
+    wav, ln = oracle.make_waveforms([16000, 5519, 160000], seed=5, dist="tilt")
+    for b in range(3):
+        x = wav[b, : ln[b]].astype(np.float64)
+        xn = x * (1.0 / (np.abs(x).max() + 1e-9))
+        y = np.concatenate([xn[:1], xn[1:] - 0.97 * xn[:-1]])
+        r64 = oracle.logmel_ref(wav[b, : ln[b]], dtype=np.float64)
+        for mel, tol in ((fb, 5e-5), (W.astype(np.float64), 5e-6)):
+            S = au.spectrogram(y, win, frame_length=400, hop_length=160, fft_length=512, power=2.0, center=False,
+                               preemphasis=None, mel_filters=mel, mel_floor=1e-9, log_mel="log10", dtype=np.float64)
+            assert S.T.shape == r64.shape                      # same frame count: 1 + (N - 400) // 160
+            assert np.abs(S.T - r64).max() <= tol, (b, np.abs(S.T - r64).max())
