@@ -335,15 +335,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const __grid_
           *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * i) = o;
         }
         __syncwarp();
+{
+          const int c4 = (lane & 7) * 4, r_lo = lane >> 3, tb = t0 + q * 32;
+          float* yb = a.y + ((size_t)b * a.T_out + tb + r_lo) * a.C_out + n0 + g * 32 + c4;
+          const float* sp = stg + r_lo * kStgStride + c4;
+          if (2 * (tb + 31) < cf && tb + 31 < a.T_out) {      // warp-uniform: all 32 rows are data rows inside the tensor
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = (lane >> 3) + 4 * i;
-          const int c4 = (lane & 7) * 4;
-          float4 o = *reinterpret_cast<const float4*>(stg + rr * kStgStride + c4);
-          const int t = t0 + q * 32 + rr;
-          if (2 * t >= cf) o = __ldg(reinterpret_cast<const float4*>(a.pad_out + n0 + g * 32 + c4));
-          if (t < a.T_out)
-            *reinterpret_cast<float4*>(a.y + ((size_t)b * a.T_out + t) * a.C_out + n0 + g * 32 + c4) = o;
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(yb + (size_t)(4 * i) * a.C_out) = *reinterpret_cast<const float4*>(sp + 4 * i * kStgStride);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int t = tb + r_lo + 4 * i;
+              float4 o = *reinterpret_cast<const float4*>(sp + 4 * i * kStgStride);
+              if (2 * t >= cf) o = __ldg(reinterpret_cast<const float4*>(a.pad_out + n0 + g * 32 + c4));
+              if (t < a.T_out) *reinterpret_cast<float4*>(yb + (size_t)(4 * i) * a.C_out) = o;
+            }
+          }
         }
       }
       tc_fence_before();
