@@ -1,8 +1,9 @@
 """CPU oracle for the Telugu-ASR front-end hot path.  TEST INFRASTRUCTURE ONLY.
 
 This package restates, on the CPU, the arithmetic of the reference's
-``SpeechFeaturizer`` (src/speech_featurizer.py) and ``Conv1DSubsamplingLayer``
-(src/models/moonshine/encoder.py:9-105).  It is the *checker* for the CUDA path:
+``SpeechFeaturizer`` (src/speech_featurizer.py), ``Conv1DSubsamplingLayer``
+(src/models/moonshine/encoder.py:9-105) and the conformer configuration's ``Conv2dSubsampling``
+(src/models/conformer/encoder.py:9-73).  It is the *checker* for the CUDA path:
 only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 ``--impl reference`` legs of ``bench.py`` may import it.  Nothing under
 ``telugu_asr_b200/`` imports it, and the product path has no CPU fallback.
@@ -35,6 +36,12 @@ from .subsampling_ref import (  # noqa: F401
     sepconv1d_ref,
     subsample_ref,
     glorot_subsampling_weights,
+)
+from .conv2d_subsampling_ref import (  # noqa: F401
+    same_pads,
+    conv2d_same_ref,
+    conv2d_subsample_ref,
+    glorot_conv2d_weights,
 )
 from .synth import make_waveforms  # noqa: F401
 from . import specaugment_ref  # noqa: F401

@@ -1,0 +1,321 @@
+// Conv2dSubsampling forward of the conformer configuration (sm_100a): two Conv2D(filters, 3x3, stride 2, "same") + ReLU.
+//
+// Replaces src/models/conformer/encoder.py:50-67 (conv1 -> relu -> conv2 -> relu -> merge_two_last_dims) for the
+// layers built at :26-48 with config/conformer.yaml:22-27 (filters 144).  Channels-last like Keras:
+//   feat [B, T, W]  (the [B,T,80,1] features)  ->  h1 [B, H1, W1, F]  ->  out [B, H2, W2*F],
+//   H1 = ceil(T/2), W1 = ceil(W/2), H2 = ceil(H1/2), W2 = ceil(W1/2); TensorFlow "SAME": the odd padding row/column
+//   goes AFTER (pad_before = pad_total / 2).
+//
+//   conv2d_first_kernel   1 -> F channels: nine FMAs per output on the CUDA cores, HBM-write bound (h1 is the big tensor);
+//   conv2d_tf32_kernel    F -> F channels as an implicit GEMM on the tensor cores: tile = 128 consecutive output
+//                         positions (i, j) of one utterance x all F filters; K runs over 9 taps x ceil(F/32) channel
+//                         chunks.  For each chunk the warps gather the 128 input rows of that tap (one coalesced 128-byte
+//                         row per position, zero outside the image), round them to TF32 and write the UMMA A operand
+//                         (K-major, SWIZZLE_128B); B = the tap's [F, 32] weight slab, packed once by the plan and fetched
+//                         with cp.async.bulk; tcgen05.mma kind::tf32 accumulates in TMEM; epilogue = bias + ReLU,
+//                         transposed through shared memory to coalesced stores.  Same pipeline skeleton as
+//                         sepconv_tf32.cu (two A/B stages, commit-released), with the depthwise producer replaced by a
+//                         gather.
+// First version (round 1): correct and on the tensor cores; conv1 is not yet fused into the producer.
+#include "sepconv_common.cuh"
+
+using namespace tasr;
+using namespace tasr_sep;
+
+struct TasrConv2dPlan {
+  int device;
+  int filters;          // F
+  int NT;               // F rounded up to a multiple of 32 (UMMA N, TMEM columns)
+  int cpt;              // 32-channel chunks per tap = ceil(F / 32)
+  float* d_w1;          // [9][F] first-layer taps (borrowed layout [3,3,1,F] flattened), copied
+  float* d_b1;          // [F]
+  float* d_b2;          // [NT] zero padded
+  float* d_bpack;       // [9*cpt][NT*32] shared-memory images of the second-layer weights
+};
+
+namespace {
+
+struct C2Args {
+  const float* h1;
+  const float* bpack;
+  const float* bias;
+  float* y;
+  int32_t H1, W1, H2, W2, F, NT, cpt, pt, pl;
+};
+
+__global__ void __launch_bounds__(256) conv2d_first_kernel(const float* __restrict__ x, const float* __restrict__ w1,
+                                                           const float* __restrict__ b1, float* __restrict__ h1,
+                                                           int B, int T, int W, int H1, int W1, int F, int pt, int pl) {
+  extern __shared__ float sw[];                      // [9][F] taps + [F] bias
+  for (int i = threadIdx.x; i < 10 * F; i += blockDim.x) sw[i] = (i < 9 * F) ? w1[i] : b1[i - 9 * F];
+  __syncthreads();
+  const int f4n = F >> 2;
+  const long long total = (long long)B * H1 * W1 * f4n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(idx % f4n) * 4;
+    long long pos = idx / f4n;
+    const int j = (int)(pos % W1); pos /= W1;
+    const int i = (int)(pos % H1);
+    const int b = (int)(pos / H1);
+    float4 acc = *reinterpret_cast<const float4*>(sw + 9 * F + f);
+    const float* xb = x + (size_t)b * T * W;
+#pragma unroll
+    for (int di = 0; di < 3; ++di) {
+      const int r = 2 * i + di - pt;
+#pragma unroll
+      for (int dj = 0; dj < 3; ++dj) {
+        const int c = 2 * j + dj - pl;
+        const float v = (r >= 0 && r < T && c >= 0 && c < W) ? __ldg(xb + (size_t)r * W + c) : 0.0f;
+        const float4 w = *reinterpret_cast<const float4*>(sw + (di * 3 + dj) * F + f);
+        acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y); acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
+      }
+    }
+    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+    *reinterpret_cast<float4*>(h1 + idx * 4) = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) conv2d_tf32_kernel(const C2Args a) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  unsigned char* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NT = a.NT, F = a.F;
+  const uint32_t bBytes = (uint32_t)NT * 128u;
+
+  unsigned char* sA = sm;                          // 2 x 16 KiB
+  unsigned char* sB = sm + 2 * kABytes;            // 2 x NT*128
+  float* sBias = reinterpret_cast<float*>(sB + 2 * bBytes);   // 256 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);  // [0,1] B full, [2,3] stage free, [4] accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), bar_u = smem_u32(bars);
+
+  const int b = blockIdx.z, t0 = blockIdx.x * kMT;
+  const int M_total = a.H2 * a.W2;
+  const int n_chunks = 9 * a.cpt;
+
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  if (tid == 32) {
+    for (int i = 0; i < 5; ++i) mbar_init(bar_u + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < NT; i += kThreads) sBias[i] = a.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t idesc = umma_idesc_tf32(kMT, NT);
+
+  // this warp's 16 output positions: top-left input coordinate of each (before the tap offset)
+  int ri[kRun], rj[kRun];
+#pragma unroll
+  for (int j = 0; j < kRun; ++j) {
+    const int m = t0 + warp * kRun + j;
+    const int oi = m / a.W2, oj = m - oi * a.W2;
+    ri[j] = (m < M_total) ? 2 * oi - a.pt : -100000;   // out-of-range position: every tap lands outside the image
+    rj[j] = 2 * oj - a.pl;
+  }
+  const float* hb = a.h1 + (size_t)b * a.H1 * a.W1 * F;
+
+  auto fetch_b = [&](int kc) {
+    const int sb = kc & 1;
+    mbar_expect_tx(bar_u + 8 * sb, bBytes);
+    bulk_g2s(sB_u + sb * bBytes, a.bpack + (size_t)kc * NT * kKC, bBytes, bar_u + 8 * sb);
+  };
+  if (tid == 0) {
+    fetch_b(0);
+    fetch_b(1);
+  }
+  for (int kc = 0; kc < n_chunks; ++kc) {
+    const int s = kc & 1, use = kc >> 1;
+    if (kc >= 2) {                       // stage s is free once the MMAs of chunk kc-2 completed
+      mbar_wait(bar_u + 8 * (2 + s), (use - 1) & 1);
+      tc_fence_after();
+    }
+    // ---- gather: tap (di, dj), channels [c0, c0+32) of the 128 positions -> A[s] ----------------
+    const int tap = kc / a.cpt, cc = kc - tap * a.cpt;
+    const int di = tap / 3, dj = tap - 3 * di;
+    const int c = cc * kKC + lane;
+    const bool cok = c < F;
+    float v[kRun];
+#pragma unroll
+    for (int j = 0; j < kRun; ++j) {
+      const int r = ri[j] + di, q = rj[j] + dj;
+      const bool ok = cok && r >= 0 && r < a.H1 && q >= 0 && q < a.W1;
+      v[j] = ok ? __ldg(hb + ((size_t)r * a.W1 + q) * F + c) : 0.0f;
+    }
+    if (tid == 0 && kc >= 1 && kc + 1 < n_chunks) {   // (the loads above are in flight while this waits)
+      mbar_wait(bar_u + 8 * (2 + (s ^ 1)), ((kc - 1) >> 1) & 1);   // MMAs of chunk kc-1 done: its B stage is free
+      fetch_b(kc + 1);
+    }
+    unsigned char* As = sA + s * kABytes;
+#pragma unroll
+    for (int j = 0; j < kRun; ++j) {
+      const int row = warp * kRun + j;
+      const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u;
+      *reinterpret_cast<uint32_t*>(As + off) = to_tf32(v[j]);
+    }
+    fence_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(bar_u + 8 * s, use & 1); // B chunk has landed
+      tc_fence_after();
+      const uint64_t da = umma_desc_sw128(sA_u + s * kABytes);
+      const uint64_t db = umma_desc_sw128(sB_u + s * bBytes);
+      for (int k = 0; k < 4; ++k)
+        umma_tf32(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+      umma_commit(bar_u + 8 * (2 + s));
+      if (kc == n_chunks - 1) umma_commit(bar_u + 8 * 4);
+    }
+  }
+
+  // ---- epilogue: TMEM -> bias + ReLU -> transpose in shared memory -> coalesced stores ----------
+  mbar_wait(bar_u + 8 * 4, 0);
+  tc_fence_after();
+  {
+    const int q = warp & 3, half = warp >> 2;
+    float* stg = reinterpret_cast<float*>(sm) + warp * (32 * kStgStride);   // aliases A/B (all MMAs done)
+    const int ngroups = NT >> 5;
+    for (int g = half; g < ngroups; g += 2) {
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32), r);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 bv = *reinterpret_cast<const float4*>(sBias + g * 32 + 4 * i);
+        float4 o;
+        o.x = fmaxf(__uint_as_float(r[4 * i + 0]) + bv.x, 0.0f);
+        o.y = fmaxf(__uint_as_float(r[4 * i + 1]) + bv.y, 0.0f);
+        o.z = fmaxf(__uint_as_float(r[4 * i + 2]) + bv.z, 0.0f);
+        o.w = fmaxf(__uint_as_float(r[4 * i + 3]) + bv.w, 0.0f);
+        *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * i) = o;
+      }
+      __syncwarp();
+      const int c4 = (lane & 7) * 4, r_lo = lane >> 3, tb = t0 + q * 32;
+      const int n = g * 32 + c4;
+      if (n < F) {                         // (F is a multiple of 4: a float4 is all inside or all outside)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = tb + r_lo + 4 * i;
+          if (m < M_total)
+            *reinterpret_cast<float4*>(a.y + ((size_t)b * M_total + m) * F + n) =
+                *reinterpret_cast<const float4*>(stg + (r_lo + 4 * i) * kStgStride + c4);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+// w2 [3,3,F,F] (Keras kernel: tap, c_in, c_out) -> per (tap, chunk) shared-memory image of B: row n (128 bytes) holds
+// input channels c0..c0+31 of filter n, 16-byte groups XOR-swizzled by (n & 7), TF32-rounded; rows n >= F and
+// channels >= F are zero.
+__global__ void pack_w2_kernel(const float* __restrict__ w2, int F, int NT, int cpt, float* __restrict__ out) {
+  const size_t total = (size_t)9 * cpt * NT * kKC;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cl = (int)(i % kKC);
+    const int n = (int)((i / kKC) % NT);
+    const int kc = (int)(i / ((size_t)kKC * NT));
+    const int tap = kc / cpt, c = (kc - tap * cpt) * kKC + cl;
+    const float v = (c < F && n < F) ? w2[((size_t)tap * F + c) * F + n] : 0.0f;
+    const size_t base = (size_t)kc * NT * kKC;
+    const int phys = n * kKC + ((((cl >> 2) ^ (n & 7)) << 2) | (cl & 3));
+    out[base + phys] = __uint_as_float(to_tf32(v));
+  }
+}
+
+size_t c2_smem_bytes(int NT) { return 1024 + 2 * kABytes + 2 * (size_t)NT * 128 + 256 * 4 + 128; }
+
+void same_pads(int n, int k, int s, int* out, int* before) {
+  *out = (n + s - 1) / s;
+  int total = (*out - 1) * s + k - n;
+  if (total < 0) total = 0;
+  *before = total / 2;
+}
+
+}  // namespace
+
+extern "C" int tasr_conv2d_plan_create(const float* w1, const float* b1, const float* w2, const float* b2, int32_t filters,
+                                       TasrConv2dPlan** out, tasr_stream_t stream) {
+  if (!w1 || !b1 || !w2 || !b2 || !out) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_plan_create: null argument");
+  *out = nullptr;
+  if (filters < 4 || (filters & 3) || filters > 256)
+    return fail(TASR_ERR_UNSUPPORTED, "tasr_conv2d_plan_create: filters=%d must be a multiple of 4 in [4,256]", filters);
+  TasrConv2dPlan* p = new TasrConv2dPlan();
+  p->filters = filters;
+  p->NT = (filters + 31) & ~31;
+  p->cpt = (filters + kKC - 1) / kKC;
+  p->d_w1 = p->d_b1 = p->d_b2 = p->d_bpack = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = check_cuda(cudaGetDevice(&p->device), "cudaGetDevice");
+  const size_t nb = (size_t)9 * p->cpt * p->NT * kKC;
+  if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_w1, (size_t)9 * filters * sizeof(float)), "cudaMalloc conv1 taps");
+  if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_b1, (size_t)filters * sizeof(float)), "cudaMalloc conv1 bias");
+  if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_b2, (size_t)p->NT * sizeof(float)), "cudaMalloc conv2 bias");
+  if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_bpack, nb * sizeof(float)), "cudaMalloc packed conv2 weights");
+  if (rc == TASR_OK) rc = check_cuda(cudaMemcpyAsync(p->d_w1, w1, (size_t)9 * filters * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy conv1 taps");
+  if (rc == TASR_OK) rc = check_cuda(cudaMemcpyAsync(p->d_b1, b1, (size_t)filters * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy conv1 bias");
+  if (rc == TASR_OK) rc = check_cuda(cudaMemsetAsync(p->d_b2, 0, (size_t)p->NT * sizeof(float), st), "clear conv2 bias");
+  if (rc == TASR_OK) rc = check_cuda(cudaMemcpyAsync(p->d_b2, b2, (size_t)filters * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy conv2 bias");
+  if (rc == TASR_OK) {
+    pack_w2_kernel<<<(unsigned)((nb + 255) / 256 > 1024 ? 1024 : (nb + 255) / 256), 256, 0, st>>>(w2, filters, p->NT, p->cpt, p->d_bpack);
+    count_launch();
+    rc = check_cuda(cudaGetLastError(), "pack_w2_kernel");
+  }
+  if (rc == TASR_OK)
+    rc = check_cuda(cudaFuncSetAttribute(conv2d_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes(256)),
+                    "cudaFuncSetAttribute(conv2d_tf32_kernel)");
+  if (rc != TASR_OK) { tasr_conv2d_plan_destroy(p); return rc; }
+  *out = p;
+  return TASR_OK;
+}
+
+extern "C" int tasr_conv2d_plan_destroy(TasrConv2dPlan* p) {
+  if (!p) return TASR_OK;
+  cudaFree(p->d_w1); cudaFree(p->d_b1); cudaFree(p->d_b2); cudaFree(p->d_bpack);
+  delete p;
+  return TASR_OK;
+}
+
+extern "C" int tasr_conv2d_output_shape(int32_t t, int32_t w, int32_t* h1, int32_t* w1, int32_t* h2, int32_t* w2) {
+  if (t < 0 || w < 0 || !h1 || !w1 || !h2 || !w2) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_output_shape: bad argument");
+  int pb;
+  same_pads(t, 3, 2, h1, &pb); same_pads(w, 3, 2, w1, &pb);
+  same_pads(*h1, 3, 2, h2, &pb); same_pads(*w1, 3, 2, w2, &pb);
+  return TASR_OK;
+}
+
+extern "C" int tasr_conv2d_subsample_tf32(const TasrConv2dPlan* p, const float* feat, int32_t B, int32_t T, int32_t W,
+                                          float* h1, float* out, tasr_stream_t stream) {
+  if (!p || !feat || !h1 || !out) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample_tf32: null argument");
+  if (B < 0 || T < 0 || W < 0) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample_tf32: negative size");
+  if (!aligned16(h1) || !aligned16(out)) return fail(TASR_ERR_MISALIGNED, "tasr_conv2d_subsample_tf32: h1/out must be 16-byte aligned");
+  int dev = 0;
+  TASR_CUDA(cudaGetDevice(&dev));
+  if (dev != p->device) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample_tf32: plan was created on device %d, current device is %d", p->device, dev);
+  if (B == 0 || T == 0 || W == 0) return TASR_OK;
+  if (B > 65535) return fail(TASR_ERR_UNSUPPORTED, "tasr_conv2d_subsample_tf32: batch > 65535");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int F = p->filters;
+  int H1, W1, H2, W2, pt1, pl1, pt2, pl2;
+  same_pads(T, 3, 2, &H1, &pt1); same_pads(W, 3, 2, &W1, &pl1);
+  same_pads(H1, 3, 2, &H2, &pt2); same_pads(W1, 3, 2, &W2, &pl2);
+  {
+    const long long total = (long long)B * H1 * W1 * (F / 4);
+    const long long blocks = (total + 255) / 256;
+    const int grid = (int)(blocks < (long long)sm_count() * 16 ? (blocks > 0 ? blocks : 1) : (long long)sm_count() * 16);
+    conv2d_first_kernel<<<grid, 256, (size_t)10 * F * sizeof(float), st>>>(feat, p->d_w1, p->d_b1, h1, B, T, W, H1, W1, F, pt1, pl1);
+    TASR_LAUNCH_CHECK("conv2d_first_kernel");
+  }
+  C2Args a;
+  a.h1 = h1; a.bpack = p->d_bpack; a.bias = p->d_b2; a.y = out;
+  a.H1 = H1; a.W1 = W1; a.H2 = H2; a.W2 = W2; a.F = F; a.NT = p->NT; a.cpt = p->cpt; a.pt = pt2; a.pl = pl2;
+  const int M_total = H2 * W2;
+  dim3 grid((M_total + kMT - 1) / kMT, 1, B);
+  conv2d_tf32_kernel<<<grid, kThreads, c2_smem_bytes(p->NT), st>>>(a);
+  TASR_LAUNCH_CHECK("conv2d_tf32_kernel");
+  return TASR_OK;
+}

@@ -910,3 +910,32 @@ def test_host_to_host_pipeline_matches_device_front_end(cuda_device, graph):
             assert torch.equal(g, w.cpu()), i
     if graph:
         assert pipe.kernels_per_submit and pipe.kernels_per_submit >= 6
+
+
+@pytest.mark.parametrize("T,B,filters", [(37, 3, 144), (38, 2, 144), (1498, 4, 144), (100, 2, 16)])
+def test_conv2d_subsampling_matches_oracle(cuda_device, T, B, filters):
+    """Conformer front end (src/models/conformer/encoder.py:9-67): two 3x3 stride-2 "same" Conv2D + ReLU on the
+    tensor cores vs the numpy oracle: max-abs error / max-abs reference <= 1e-3 (TF32 operands, K = 9*filters),
+    output shape [B, ceil(ceil(T/2)/2), 20*filters], lengths = ceil(L/2) bit-exact (applied once, like the reference)."""
+    rng = np.random.default_rng(T + filters)
+    x = rng.standard_normal((B, T, 80, 1)).astype(np.float32) * 2.0 - 1.0
+    lens = np.array([T] + [max(1, T // (b + 2)) for b in range(B - 1)], dtype=np.int32)
+    for b in range(B):
+        x[b, lens[b]:] = 0.0                            # collate padding
+    ws = oracle.glorot_conv2d_weights(filters, seed=5)
+    layer = tasr.Conv2dSubsampling({"name": "conv2d", "filters": filters, "kernel_size": 3, "strides": 2, "padding": "same"})
+    layer.set_weights(ws, cuda_device)
+    out, out_len = _call_or_skip(layer, [gpu(x, cuda_device), gpu(lens, cuda_device)])
+    torch.cuda.synchronize()
+    ref, ref_len = oracle.conv2d_subsample_ref(x, lens, ws, dtype=np.float64)
+    assert tuple(out.shape) == ref.shape == layer.compute_output_shape((B, T, 80, 1))
+    np.testing.assert_array_equal(out_len.cpu().numpy(), ref_len)
+    o = out.cpu().numpy()
+    assert np.isfinite(o).all()
+    rel = np.abs(o - ref).max() / np.abs(ref).max()
+    assert rel <= SUB_TOL_TF32, rel
+    # construction-time behaviour
+    with pytest.raises(NotImplementedError):
+        tasr.Conv2dSubsampling({"filters": 144, "kernel_size": 5})
+    with pytest.raises(ValueError):
+        layer.set_weights([(ws[0][0][:2], ws[0][1]), ws[1]], cuda_device)

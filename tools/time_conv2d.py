@@ -1,0 +1,27 @@
+"""Device time of Conv2dSubsampling (conformer front end, filters 144) on the bench batch's feature shape
+[256, 1498, 80, 1].  Development aid, run under gpurun:  python tools/time_conv2d.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import telugu_asr_b200 as tasr
+
+dev = torch.device("cuda:0")
+B, T = int(sys.argv[1]) if len(sys.argv) > 1 else 256, 1498
+layer = tasr.Conv2dSubsampling({"filters": 144, "kernel_size": 3, "strides": 2, "padding": "same"}, seed=1)
+layer.build(dev)
+x = torch.randn((B, T, 80, 1), device=dev)
+ln = torch.full((B,), T, dtype=torch.int32, device=dev)
+for _ in range(3):
+    out, _ = layer([x, ln])
+torch.cuda.synchronize()
+ts = []
+for _ in range(10):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); out, _ = layer([x, ln]); b.record(); torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+ts.sort()
+h1, w1, h2, w2 = layer.output_shape(T, 80)
+flop = 2.0 * B * h2 * w2 * 144 * 9 * 144 + 2.0 * B * h1 * w1 * 144 * 9
+audio_s = B * (400 + 160 * (T - 1)) / 16000
+print(f"Conv2dSubsampling B={B} T={T}: med {ts[len(ts)//2]:.3f} ms  min {ts[0]:.3f} ms; out {tuple(out.shape)}; "
+      f"{flop / ts[len(ts)//2] / 1e9:.1f} TFLOP/s; {audio_s / ts[len(ts)//2] * 1e3 / 1e6:.2f} M audio-s/s for this stage")
