@@ -126,25 +126,29 @@ __global__ void __launch_bounds__(kThreads, 2) conv2d_tf32_kernel(const C2Args a
     fetch_b(0);
     fetch_b(1);
   }
-  for (int kc = 0; kc < n_chunks; ++kc) {
-    const int s = kc & 1, use = kc >> 1;
-    if (kc >= 2) {                       // stage s is free once the MMAs of chunk kc-2 completed
-      mbar_wait(bar_u + 8 * (2 + s), (use - 1) & 1);
-      tc_fence_after();
-    }
-    // ---- gather: tap (di, dj), channels [c0, c0+32) of the 128 positions -> A[s] ----------------
+  // gather of one chunk: tap (di, dj), channels [c0, c0+32) of this warp's 16 positions (zero outside the image)
+  auto gather = [&](int kc, float (&v)[kRun]) {
     const int tap = kc / a.cpt, cc = kc - tap * a.cpt;
     const int di = tap / 3, dj = tap - 3 * di;
     const int c = cc * kKC + lane;
     const bool cok = c < F;
-    float v[kRun];
 #pragma unroll
     for (int j = 0; j < kRun; ++j) {
       const int r = ri[j] + di, q = rj[j] + dj;
       const bool ok = cok && r >= 0 && r < a.H1 && q >= 0 && q < a.W1;
       v[j] = ok ? __ldg(hb + ((size_t)r * a.W1 + q) * F + c) : 0.0f;
     }
-    if (tid == 0 && kc >= 1 && kc + 1 < n_chunks) {   // (the loads above are in flight while this waits)
+  };
+  float v[kRun], vn[kRun];
+  gather(0, v);
+  for (int kc = 0; kc < n_chunks; ++kc) {
+    const int s = kc & 1, use = kc >> 1;
+    if (kc + 1 < n_chunks) gather(kc + 1, vn);   // next chunk's rows are in flight while this one is stored and multiplied
+    if (kc >= 2) {                       // stage s is free once the MMAs of chunk kc-2 completed
+      mbar_wait(bar_u + 8 * (2 + s), (use - 1) & 1);
+      tc_fence_after();
+    }
+    if (tid == 0 && kc >= 1 && kc + 1 < n_chunks) {
       mbar_wait(bar_u + 8 * (2 + (s ^ 1)), ((kc - 1) >> 1) & 1);   // MMAs of chunk kc-1 done: its B stage is free
       fetch_b(kc + 1);
     }
@@ -167,6 +171,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv2d_tf32_kernel(const C2Args a
       umma_commit(bar_u + 8 * (2 + s));
       if (kc == n_chunks - 1) umma_commit(bar_u + 8 * 4);
     }
+#pragma unroll
+    for (int j = 0; j < kRun; ++j) v[j] = vn[j];
   }
 
   // ---- epilogue: TMEM -> bias + ReLU -> transpose in shared memory -> coalesced stores ----------
