@@ -9,13 +9,13 @@
 //   conv2d_first_kernel   1 -> F channels: nine FMAs per output on the CUDA cores, HBM-write bound (h1 is the big tensor);
 //   conv2d_tf32_kernel    F -> F channels as an implicit GEMM on the tensor cores: tile = 128 consecutive output
 //                         positions (i, j) of one utterance x all F filters; K runs over 9 taps x ceil(F/32) channel
-//                         chunks.  For each chunk the warps gather the 128 input rows of that tap (one coalesced 128-byte
-//                         row per position, zero outside the image), round them to TF32 and write the UMMA A operand
-//                         (K-major, SWIZZLE_128B); B = the tap's [F, 32] weight slab, packed once by the plan and fetched
+//                         chunks.  For each chunk the 128 input rows of that tap (one 128-byte row per position, zero
+//                         outside the image; h1 is stored TF32-rounded by the first kernel) are gathered with cp.async
+//                         straight into the UMMA A operand tile (K-major, SWIZZLE_128B), two chunks ahead of the MMAs; B = the tap's [F, 32] weight slab, packed once by the plan and fetched
 //                         with cp.async.bulk; tcgen05.mma kind::tf32 accumulates in TMEM; epilogue = bias + ReLU,
 //                         transposed through shared memory to coalesced stores.  Same pipeline skeleton as
-//                         sepconv_tf32.cu (two A/B stages, commit-released), with the depthwise producer replaced by a
-//                         gather.
+//                         sepconv_tf32.cu (A/B stage ring, commit-released), with the depthwise producer replaced by an
+//                         asynchronous gather.
 // First version (round 1): correct and on the tensor cores; conv1 is not yet fused into the producer.
 #include "sepconv_common.cuh"
 
@@ -70,9 +70,19 @@ __global__ void __launch_bounds__(256) conv2d_first_kernel(const float* __restri
         acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y); acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
       }
     }
-    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+    // ReLU, then rounded to TF32 (rna) HERE: h1 is only ever read as the A operand of the tensor-core GEMM, so the
+    // second kernel can move its rows into the operand tiles with plain asynchronous copies.
+    acc.x = __uint_as_float(to_tf32(fmaxf(acc.x, 0.f))); acc.y = __uint_as_float(to_tf32(fmaxf(acc.y, 0.f)));
+    acc.z = __uint_as_float(to_tf32(fmaxf(acc.z, 0.f))); acc.w = __uint_as_float(to_tf32(fmaxf(acc.w, 0.f)));
     *reinterpret_cast<float4*>(h1 + idx * 4) = acc;
   }
+}
+
+constexpr int kC2Stages = 3;             // A / B stage ring depth (3 x (16 + 20) KB: two CTAs per SM)
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;   // src-size 0: the 16 destination bytes are zero-filled, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
 
 __global__ void __launch_bounds__(kThreads, 2) conv2d_tf32_kernel(const C2Args a) {
@@ -83,12 +93,15 @@ __global__ void __launch_bounds__(kThreads, 2) conv2d_tf32_kernel(const C2Args a
   const int NT = a.NT, F = a.F;
   const uint32_t bBytes = (uint32_t)NT * 128u;
 
-  unsigned char* sA = sm;                          // 2 x 16 KiB
-  unsigned char* sB = sm + 2 * kABytes;            // 2 x NT*128
-  float* sBias = reinterpret_cast<float*>(sB + 2 * bBytes);   // 256 floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);  // [0,1] B full, [2,3] stage free, [4] accumulator
+  unsigned char* sA = sm;                                     // kC2Stages x 16 KiB
+  unsigned char* sB = sm + kC2Stages * kABytes;               // kC2Stages x NT*128
+  float* sBias = reinterpret_cast<float*>(sB + kC2Stages * bBytes);   // 256 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);  // [0..2] B full, [3..5] stage free, [6] accumulator
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), bar_u = smem_u32(bars);
+  auto bar_bfull = [&](int s) { return bar_u + 8u * (uint32_t)s; };
+  auto bar_free = [&](int s) { return bar_u + 8u * (uint32_t)(kC2Stages + s); };
+  const uint32_t bar_acc = bar_u + 8u * (uint32_t)(2 * kC2Stages);
 
   const int b = blockIdx.z, t0 = blockIdx.x * kMT;
   const int M_total = a.H2 * a.W2;
@@ -96,7 +109,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv2d_tf32_kernel(const C2Args a
 
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   if (tid == 32) {
-    for (int i = 0; i < 5; ++i) mbar_init(bar_u + 8 * i, 1);
+    for (int i = 0; i < 2 * kC2Stages + 1; ++i) mbar_init(bar_u + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < NT; i += kThreads) sBias[i] = a.bias[i];
@@ -106,81 +119,86 @@ __global__ void __launch_bounds__(kThreads, 2) conv2d_tf32_kernel(const C2Args a
   const uint32_t tmem = *tmem_slot;
   const uint32_t idesc = umma_idesc_tf32(kMT, NT);
 
-  // this warp's 16 output positions: top-left input coordinate of each (before the tap offset)
-  int ri[kRun], rj[kRun];
+  // Each thread moves four 16-byte pieces per chunk: piece p = tid + 256 i -> row p >> 3 (= tid/8 + 32 i) of the tile,
+  // 16-byte group p & 7 (= tid & 7: four channels) of the row.  Top-left input coordinate of its four rows:
+  const int grp = tid & 7;
+  int ri[4], rj[4];
+  uint32_t dst_off[4];
 #pragma unroll
-  for (int j = 0; j < kRun; ++j) {
-    const int m = t0 + warp * kRun + j;
+  for (int i = 0; i < 4; ++i) {
+    const int row = (tid >> 3) + 32 * i;
+    const int m = t0 + row;
     const int oi = m / a.W2, oj = m - oi * a.W2;
-    ri[j] = (m < M_total) ? 2 * oi - a.pt : -100000;   // out-of-range position: every tap lands outside the image
-    rj[j] = 2 * oj - a.pl;
+    ri[i] = (m < M_total) ? 2 * oi - a.pt : -100000;   // out-of-range position: every tap lands outside the image
+    rj[i] = 2 * oj - a.pl;
+    dst_off[i] = (uint32_t)row * 128u + (uint32_t)((grp ^ (row & 7)) << 4);   // UMMA K-major SWIZZLE_128B
   }
   const float* hb = a.h1 + (size_t)b * a.H1 * a.W1 * F;
 
-  auto fetch_b = [&](int kc) {
-    const int sb = kc & 1;
-    mbar_expect_tx(bar_u + 8 * sb, bBytes);
-    bulk_g2s(sB_u + sb * bBytes, a.bpack + (size_t)kc * NT * kKC, bBytes, bar_u + 8 * sb);
-  };
-  if (tid == 0) {
-    fetch_b(0);
-    fetch_b(1);
-  }
-  // gather of one chunk: tap (di, dj), channels [c0, c0+32) of this warp's 16 positions (zero outside the image)
-  auto gather = [&](int kc, float (&v)[kRun]) {
+  // h1 already holds TF32-rounded values: the A operand of a chunk — tap (di, dj), channels [32 cc, 32 cc + 32) of
+  // the 128 positions — is gathered with cp.async straight into the swizzled tile (zero-filled outside the image /
+  // beyond the last channel), kC2Stages - 1 chunks ahead of the MMAs; nothing passes through registers.
+  auto issue_a = [&](int kc) {
     const int tap = kc / a.cpt, cc = kc - tap * a.cpt;
     const int di = tap / 3, dj = tap - 3 * di;
-    const int c = cc * kKC + lane;
+    const int c = cc * kKC + 4 * grp;
     const bool cok = c < F;
+    const uint32_t base = sA_u + (uint32_t)(kc % kC2Stages) * kABytes;
 #pragma unroll
-    for (int j = 0; j < kRun; ++j) {
-      const int r = ri[j] + di, q = rj[j] + dj;
+    for (int i = 0; i < 4; ++i) {
+      const int r = ri[i] + di, q = rj[i] + dj;
       const bool ok = cok && r >= 0 && r < a.H1 && q >= 0 && q < a.W1;
-      v[j] = ok ? __ldg(hb + ((size_t)r * a.W1 + q) * F + c) : 0.0f;
+      const float* src = ok ? hb + ((size_t)r * a.W1 + q) * F + c : hb;
+      cp_async16_zfill(base + dst_off[i], src, ok);
     }
   };
-  float v[kRun], vn[kRun];
-  gather(0, v);
+  auto fetch_b = [&](int kc) {
+    const int sb = kc % kC2Stages;
+    mbar_expect_tx(bar_bfull(sb), bBytes);
+    bulk_g2s(sB_u + sb * bBytes, a.bpack + (size_t)kc * NT * kKC, bBytes, bar_bfull(sb));
+  };
+  for (int kc = 0; kc < kC2Stages - 1; ++kc) {
+    if (kc < n_chunks) {
+      issue_a(kc);
+      if (tid == 0) fetch_b(kc);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (int kc = 0; kc < n_chunks; ++kc) {
-    const int s = kc & 1, use = kc >> 1;
-    if (kc + 1 < n_chunks) gather(kc + 1, vn);   // next chunk's rows are in flight while this one is stored and multiplied
-    if (kc >= 2) {                       // stage s is free once the MMAs of chunk kc-2 completed
-      mbar_wait(bar_u + 8 * (2 + s), (use - 1) & 1);
-      tc_fence_after();
-    }
-    if (tid == 0 && kc >= 1 && kc + 1 < n_chunks) {
-      mbar_wait(bar_u + 8 * (2 + (s ^ 1)), ((kc - 1) >> 1) & 1);   // MMAs of chunk kc-1 done: its B stage is free
-      fetch_b(kc + 1);
-    }
-    unsigned char* As = sA + s * kABytes;
-#pragma unroll
-    for (int j = 0; j < kRun; ++j) {
-      const int row = warp * kRun + j;
-      const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u;
-      *reinterpret_cast<uint32_t*>(As + off) = to_tf32(v[j]);
-    }
-    fence_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
+    const int s = kc % kC2Stages, use = kc / kC2Stages;
+    asm volatile("cp.async.wait_group %0;" ::"n"(kC2Stages - 2) : "memory");   // this thread's pieces of chunk kc have landed
+    fence_async_smem();                  // generic-proxy (cp.async) writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) {
-      mbar_wait(bar_u + 8 * s, use & 1); // B chunk has landed
+      mbar_wait(bar_bfull(s), use & 1);  // B chunk has landed
       tc_fence_after();
       const uint64_t da = umma_desc_sw128(sA_u + s * kABytes);
       const uint64_t db = umma_desc_sw128(sB_u + s * bBytes);
       for (int k = 0; k < 4; ++k)
         umma_tf32(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
-      umma_commit(bar_u + 8 * (2 + s));
-      if (kc == n_chunks - 1) umma_commit(bar_u + 8 * 4);
+      umma_commit(bar_free(s));
+      if (kc == n_chunks - 1) umma_commit(bar_acc);
     }
-#pragma unroll
-    for (int j = 0; j < kRun; ++j) v[j] = vn[j];
+    // refill: chunk kc + kC2Stages - 1 goes into the stage chunk kc - 1 used, once its MMAs have completed (they were
+    // issued an iteration ago, and chunk kc's are already queued behind them: the tensor pipe does not idle)
+    const int nk = kc + kC2Stages - 1;
+    if (nk < n_chunks) {
+      if (kc >= 1) {
+        mbar_wait(bar_free((kc - 1) % kC2Stages), ((kc - 1) / kC2Stages) & 1);
+        tc_fence_after();
+      }
+      issue_a(nk);
+      if (tid == 0) fetch_b(nk);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
   // ---- epilogue: TMEM -> bias + ReLU -> transpose in shared memory -> coalesced stores ----------
-  mbar_wait(bar_u + 8 * 4, 0);
+  mbar_wait(bar_acc, 0);
   tc_fence_after();
   {
     const int q = warp & 3, half = warp >> 2;
-    float* stg = reinterpret_cast<float*>(sm) + warp * (32 * kStgStride);   // aliases A/B (all MMAs done)
+    float* stg = reinterpret_cast<float*>(sm) + warp * (32 * kStgStride);   // aliases A/B (all MMAs done, no copy in flight)
     const int ngroups = NT >> 5;
     for (int g = half; g < ngroups; g += 2) {
       uint32_t r[32];
@@ -233,7 +251,7 @@ __global__ void pack_w2_kernel(const float* __restrict__ w2, int F, int NT, int 
   }
 }
 
-size_t c2_smem_bytes(int NT) { return 1024 + 2 * kABytes + 2 * (size_t)NT * 128 + 256 * 4 + 128; }
+size_t c2_smem_bytes(int NT) { return 1024 + kC2Stages * kABytes + kC2Stages * (size_t)NT * 128 + 256 * 4 + 128; }
 
 void same_pads(int n, int k, int s, int* out, int* before) {
   *out = (n + s - 1) / s;
