@@ -6,7 +6,8 @@
 //   H1 = ceil(T/2), W1 = ceil(W/2), H2 = ceil(H1/2), W2 = ceil(W1/2); TensorFlow "SAME": the odd padding row/column
 //   goes AFTER (pad_before = pad_total / 2).
 //
-//   conv2d_first_kernel   1 -> F channels: nine FMAs per output on the CUDA cores, HBM-write bound (h1 is the big tensor);
+//   conv2d_first_kernel   1 -> F channels: nine FMAs per output on the CUDA cores from a zero-bordered shared-memory window,
+//                         weights in registers; bound by writing h1 (the big tensor), stored ReLU'd and TF32-rounded;
 //   conv2d_tf32_kernel    F -> F channels as an implicit GEMM on the tensor cores: tile = 128 consecutive output
 //                         positions (i, j) of one utterance x all F filters; K runs over 9 taps x ceil(F/32) channel
 //                         chunks.  For each chunk the 128 input rows of that tap (one 128-byte row per position, zero
@@ -43,38 +44,50 @@ struct C2Args {
   int32_t H1, W1, H2, W2, F, NT, cpt, pt, pl;
 };
 
-__global__ void __launch_bounds__(256) conv2d_first_kernel(const float* __restrict__ x, const float* __restrict__ w1,
-                                                           const float* __restrict__ b1, float* __restrict__ h1,
-                                                           int B, int T, int W, int H1, int W1, int F, int pt, int pl) {
-  extern __shared__ float sw[];                      // [9][F] taps + [F] bias
-  for (int i = threadIdx.x; i < 10 * F; i += blockDim.x) sw[i] = (i < 9 * F) ? w1[i] : b1[i - 9 * F];
-  __syncthreads();
+// conv1: one block = kC1Rows output rows of one utterance.  The 2*kC1Rows+1 input rows it needs are staged once in
+// shared memory with a zero border (no bounds tests in the loop); thread <-> (one of 8 positions, 4 consecutive
+// filters), its nine float4 tap weights and bias live in registers for the whole block.
+constexpr int kC1Rows = 8;
+__global__ void __launch_bounds__(512) conv2d_first_kernel(const float* __restrict__ x, const float* __restrict__ w1,
+                                                            const float* __restrict__ b1, float* __restrict__ h1,
+                                                            int T, int W, int H1, int W1, int F, int pt, int pl) {
+  extern __shared__ float xs[];                      // [2*kC1Rows+1][SW], SW = 2*W1+1 columns starting at column -pl
+  const int SW = 2 * W1 + 1;
+  const int b = blockIdx.y, i0 = blockIdx.x * kC1Rows;
+  const int nrows = min(kC1Rows, H1 - i0);
+  const float* xb = x + (size_t)b * T * W;
+  for (int k = threadIdx.x; k < (2 * kC1Rows + 1) * SW; k += blockDim.x) {
+    const int d = k / SW, cc = k - d * SW;
+    const int r = 2 * i0 + d - pt, c = cc - pl;
+    xs[k] = (r >= 0 && r < T && c >= 0 && c < W) ? __ldg(xb + (size_t)r * W + c) : 0.0f;
+  }
   const int f4n = F >> 2;
-  const long long total = (long long)B * H1 * W1 * f4n;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int f = (int)(idx % f4n) * 4;
-    long long pos = idx / f4n;
-    const int j = (int)(pos % W1); pos /= W1;
-    const int i = (int)(pos % H1);
-    const int b = (int)(pos / H1);
-    float4 acc = *reinterpret_cast<const float4*>(sw + 9 * F + f);
-    const float* xb = x + (size_t)b * T * W;
+  const int f = (threadIdx.x % f4n) * 4, p0 = threadIdx.x / f4n;
+  float4 w[9];
 #pragma unroll
-    for (int di = 0; di < 3; ++di) {
-      const int r = 2 * i + di - pt;
+  for (int k = 0; k < 9; ++k) w[k] = __ldg(reinterpret_cast<const float4*>(w1 + k * F + f));
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(b1 + f));
+  __syncthreads();
+  for (int r = 0; r < nrows; ++r) {
+    float* orow = h1 + (((size_t)b * H1 + i0 + r) * W1) * F + f;
+    for (int j = p0; j < W1; j += 8) {
+      float4 acc = bias;
 #pragma unroll
-      for (int dj = 0; dj < 3; ++dj) {
-        const int c = 2 * j + dj - pl;
-        const float v = (r >= 0 && r < T && c >= 0 && c < W) ? __ldg(xb + (size_t)r * W + c) : 0.0f;
-        const float4 w = *reinterpret_cast<const float4*>(sw + (di * 3 + dj) * F + f);
-        acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y); acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
+      for (int di = 0; di < 3; ++di) {
+        const float* xr = xs + (2 * r + di) * SW + 2 * j;
+#pragma unroll
+        for (int dj = 0; dj < 3; ++dj) {
+          const float v = xr[dj];
+          const float4 ww = w[di * 3 + dj];
+          acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y); acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
+        }
       }
+      // ReLU, then rounded to TF32 (rna) HERE: h1 is only ever read as the A operand of the tensor-core GEMM, so the
+      // second kernel can move its rows into the operand tiles with plain asynchronous copies.
+      acc.x = __uint_as_float(to_tf32(fmaxf(acc.x, 0.f))); acc.y = __uint_as_float(to_tf32(fmaxf(acc.y, 0.f)));
+      acc.z = __uint_as_float(to_tf32(fmaxf(acc.z, 0.f))); acc.w = __uint_as_float(to_tf32(fmaxf(acc.w, 0.f)));
+      *reinterpret_cast<float4*>(orow + (size_t)j * F) = acc;
     }
-    // ReLU, then rounded to TF32 (rna) HERE: h1 is only ever read as the A operand of the tensor-core GEMM, so the
-    // second kernel can move its rows into the operand tiles with plain asynchronous copies.
-    acc.x = __uint_as_float(to_tf32(fmaxf(acc.x, 0.f))); acc.y = __uint_as_float(to_tf32(fmaxf(acc.y, 0.f)));
-    acc.z = __uint_as_float(to_tf32(fmaxf(acc.z, 0.f))); acc.w = __uint_as_float(to_tf32(fmaxf(acc.w, 0.f)));
-    *reinterpret_cast<float4*>(h1 + idx * 4) = acc;
   }
 }
 
@@ -328,10 +341,10 @@ extern "C" int tasr_conv2d_subsample_tf32(const TasrConv2dPlan* p, const float* 
   same_pads(T, 3, 2, &H1, &pt1); same_pads(W, 3, 2, &W1, &pl1);
   same_pads(H1, 3, 2, &H2, &pt2); same_pads(W1, 3, 2, &W2, &pl2);
   {
-    const long long total = (long long)B * H1 * W1 * (F / 4);
-    const long long blocks = (total + 255) / 256;
-    const int grid = (int)(blocks < (long long)sm_count() * 16 ? (blocks > 0 ? blocks : 1) : (long long)sm_count() * 16);
-    conv2d_first_kernel<<<grid, 256, (size_t)10 * F * sizeof(float), st>>>(feat, p->d_w1, p->d_b1, h1, B, T, W, H1, W1, F, pt1, pl1);
+    dim3 grid1((H1 + kC1Rows - 1) / kC1Rows, B);
+    const size_t smem1 = (size_t)(2 * kC1Rows + 1) * (2 * W1 + 1) * sizeof(float);
+    if (smem1 > 48 * 1024) return fail(TASR_ERR_UNSUPPORTED, "tasr_conv2d_subsample_tf32: feature width %d too large", W);
+    conv2d_first_kernel<<<grid1, 8 * (F / 4), smem1, st>>>(feat, p->d_w1, p->d_b1, h1, T, W, H1, W1, F, pt1, pl1);
     TASR_LAUNCH_CHECK("conv2d_first_kernel");
   }
   C2Args a;
