@@ -224,19 +224,21 @@ int tasr_conv_lengths_mask(const int32_t* len_in, int32_t batch, int32_t n_layer
 /* Conv2dSubsampling of the conformer configuration (src/models/conformer/encoder.py:9-67, config/conformer.yaml:22-27):
  * two tf.keras.layers.Conv2D(filters, 3, strides 2, padding "same") each followed by ReLU, then merge_two_last_dims
  * (src/utils/math_util.py:34-46).  Weights in Keras shapes, float32 on the DEVICE: w1 [3,3,1,filters], b1 [filters],
- * w2 [3,3,filters,filters], b2 [filters]; the plan copies / packs them (w2 rounded to TF32 as UMMA tiles).
+ * w2 [3,3,filters,filters], b2 [filters]; the plan copies / packs them (w2 rounded to FP16 as UMMA tiles); filters
+ * must be a multiple of 8.
  * feat [batch, t, w] (the [B,T,80,1] features) -> out [batch, h2, w2*filters] with h1 = ceil(t/2), h2 = ceil(h1/2),
- * w1 = ceil(w/2), w2 = ceil(w1/2) (tasr_conv2d_output_shape); h1_workspace [batch, h1, w1, filters] float32 is
- * caller-provided scratch.  TensorFlow "SAME" padding (the odd row / column goes after).  The second convolution is an
- * implicit GEMM on tcgen05 (kind::tf32, FP32 accumulate).  The reference passes the lengths through
+ * w1 = ceil(w/2), w2 = ceil(w1/2) (tasr_conv2d_output_shape); h1_workspace [batch, h1, w1, filters] of 2-byte
+ * elements (FP16; 16-byte aligned) is caller-provided scratch.  TensorFlow "SAME" padding (the odd row / column goes after).  The second convolution is an
+ * implicit GEMM on tcgen05 (kind::f16: the first layer's ReLU output and w2 as FP16 — 11 significant bits, like
+ * TF32 — with FP32 accumulation).  The reference passes the lengths through
  * get_conv_length ONCE (encoder.py:59-64: ceil(L/2)): use tasr_conv_lengths_mask with one "same" layer (k 3, s 2). */
 typedef struct TasrConv2dPlan TasrConv2dPlan;
 int tasr_conv2d_plan_create(const float* w1, const float* b1, const float* w2, const float* b2, int32_t filters,
                             TasrConv2dPlan** out, tasr_stream_t stream);
 int tasr_conv2d_plan_destroy(TasrConv2dPlan* plan);
 int tasr_conv2d_output_shape(int32_t t, int32_t w, int32_t* h1, int32_t* w1, int32_t* h2, int32_t* w2);
-int tasr_conv2d_subsample_tf32(const TasrConv2dPlan* plan, const float* feat, int32_t batch, int32_t t, int32_t w,
-                               float* h1_workspace, float* out, tasr_stream_t stream);
+int tasr_conv2d_subsample(const TasrConv2dPlan* plan, const float* feat, int32_t batch, int32_t t, int32_t w,
+                               void* h1_workspace, float* out, tasr_stream_t stream);
 
 /* SpecAugment, deterministic half (replaces FreqMasking.augment / TimeMasking.augment,
  * src/augmentations/specaugment.py:6-62, applied per utterance at src/dataset.py:172): in place on

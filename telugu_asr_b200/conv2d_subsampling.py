@@ -4,7 +4,7 @@ Same constructor (`subsampling_config` with filters / kernel_size / strides / pa
 regularizer / initializer kwargs accepted), same call convention `layer([outputs, outputs_length], training=False)
 -> (outputs [B, T'', F''*filters], outputs_length)`: conv1 -> relu -> conv2 -> relu -> merge_two_last_dims, the
 lengths passed through get_conv_length ONCE (encoder.py:59-64 — ceil(L/2), although time shrinks by four; kept).
-The second convolution (filters -> filters, 9 taps) runs as an implicit GEMM on tcgen05 (TF32 operands, FP32
+The second convolution (filters -> filters, 9 taps) runs as an implicit GEMM on tcgen05 (FP16 operands, FP32
 accumulate); everything runs in libtasr_b200.so, there is no CPU path.  Only the reference configuration's geometry is
 built: kernel_size 3, strides 2, padding "same"."""
 from __future__ import annotations
@@ -115,12 +115,12 @@ class Conv2dSubsampling:
         x = x.contiguous()
         h1, w1, h2, w2 = self.output_shape(T, W)
         F = self.filter
-        work = _native.empty((B, h1, w1, F), torch.float32, x.device)
+        work = _native.empty((B, h1, w1, F), torch.float16, x.device)   # conv1's output: FP16, only the tensor cores read it
         out = _native.empty((B, h2, w2 * F), torch.float32, x.device)
         L = _native.lib()
         with torch.cuda.device(x.device):
             st = _native.stream_ptr()
-            _native.check(L.tasr_conv2d_subsample_tf32(self._plan, x.data_ptr(), B, T, W, work.data_ptr(), out.data_ptr(), st))
+            _native.check(L.tasr_conv2d_subsample(self._plan, x.data_ptr(), B, T, W, work.data_ptr(), out.data_ptr(), st))
             out_len = None
             if outputs_length is not None:
                 ln = _native.require_cuda(outputs_length, "outputs_length").to(torch.int32).contiguous()

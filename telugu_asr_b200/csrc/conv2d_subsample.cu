@@ -8,7 +8,7 @@
 //
 //   conv2d_first_kernel   1 -> F channels: nine FMAs per output on the CUDA cores from a zero-bordered shared-memory window,
 //                         weights in registers; bound by writing h1 (the big tensor), stored ReLU'd and TF32-rounded;
-//   conv2d_tf32_kernel    F -> F channels as an implicit GEMM on the tensor cores: tile = 128 consecutive output
+//   conv2d_f16_kernel    F -> F channels as an implicit GEMM on the tensor cores: tile = 128 consecutive output
 //                         positions (i, j) of one utterance x all F filters; K runs over 9 taps x ceil(F/32) channel
 //                         chunks.  For each chunk the 128 input rows of that tap (one 128-byte row per position, zero
 //                         outside the image; h1 is stored TF32-rounded by the first kernel) are gathered with cp.async
@@ -19,6 +19,7 @@
 //                         asynchronous gather.
 // First version (round 1): correct and on the tensor cores; conv1 is not yet fused into the producer.
 #include "sepconv_common.cuh"
+#include <cuda_fp16.h>
 
 using namespace tasr;
 using namespace tasr_sep;
@@ -27,17 +28,17 @@ struct TasrConv2dPlan {
   int device;
   int filters;          // F
   int NT;               // F rounded up to a multiple of 32 (UMMA N, TMEM columns)
-  int cpt;              // 32-channel chunks per tap = ceil(F / 32)
+  int cpt;              // 64-channel chunks per tap = ceil(F / 64)
   float* d_w1;          // [9][F] first-layer taps (borrowed layout [3,3,1,F] flattened), copied
   float* d_b1;          // [F]
   float* d_b2;          // [NT] zero padded
-  float* d_bpack;       // [9*cpt][NT*32] shared-memory images of the second-layer weights
+  float* d_bpack;       // [9*cpt][NT*64 halves = NT*32 floats] shared-memory images of the second-layer weights (FP16)
 };
 
 namespace {
 
 struct C2Args {
-  const float* h1;
+  const __half* h1;
   const float* bpack;
   const float* bias;
   float* y;
@@ -49,7 +50,7 @@ struct C2Args {
 // filters), its nine float4 tap weights and bias live in registers for the whole block.
 constexpr int kC1Rows = 8;
 __global__ void __launch_bounds__(512) conv2d_first_kernel(const float* __restrict__ x, const float* __restrict__ w1,
-                                                            const float* __restrict__ b1, float* __restrict__ h1,
+                                                            const float* __restrict__ b1, __half* __restrict__ h1,
                                                             int T, int W, int H1, int W1, int F, int pt, int pl) {
   extern __shared__ float xs[];                      // [2*kC1Rows+1][SW], SW = 2*W1+1 columns starting at column -pl
   const int SW = 2 * W1 + 1;
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(512) conv2d_first_kernel(const float* __restri
   const float4 bias = __ldg(reinterpret_cast<const float4*>(b1 + f));
   __syncthreads();
   for (int r = 0; r < nrows; ++r) {
-    float* orow = h1 + (((size_t)b * H1 + i0 + r) * W1) * F + f;
+    __half* orow = h1 + (((size_t)b * H1 + i0 + r) * W1) * F + f;
     for (int j = p0; j < W1; j += 8) {
       float4 acc = bias;
 #pragma unroll
@@ -82,23 +83,42 @@ __global__ void __launch_bounds__(512) conv2d_first_kernel(const float* __restri
           acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y); acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
         }
       }
-      // ReLU, then rounded to TF32 (rna) HERE: h1 is only ever read as the A operand of the tensor-core GEMM, so the
-      // second kernel can move its rows into the operand tiles with plain asynchronous copies.
-      acc.x = __uint_as_float(to_tf32(fmaxf(acc.x, 0.f))); acc.y = __uint_as_float(to_tf32(fmaxf(acc.y, 0.f)));
-      acc.z = __uint_as_float(to_tf32(fmaxf(acc.z, 0.f))); acc.w = __uint_as_float(to_tf32(fmaxf(acc.w, 0.f)));
-      *reinterpret_cast<float4*>(orow + (size_t)j * F) = acc;
+      // ReLU, then rounded to FP16 (round-to-nearest-even; 11 significant bits like TF32, and the values — ReLU of a
+      // 9-tap sum of log-mel features — are far inside its range) HERE: h1 is only ever read as the A operand of the
+      // tensor-core GEMM, so the second kernel moves its rows into the operand tiles with plain asynchronous copies,
+      // and the big tensor costs half the bytes.
+      const __half2 lo = __floats2half2_rn(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f));
+      const __half2 hi = __floats2half2_rn(fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(orow + (size_t)j * F) = pk;
     }
   }
 }
 
 constexpr int kC2Stages = 3;             // A / B stage ring depth (3 x (16 + 20) KB: two CTAs per SM)
+constexpr int kC2KC = 64;                // input channels per chunk: one 128-byte swizzle row of FP16
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, FP16 inputs, FP32 accumulate (K = 16 per instruction).
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Instruction descriptor: D=F32, A=B=F16 (format 0), both K-major, N, M.
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
   const uint32_t n = valid ? 16u : 0u;   // src-size 0: the 16 destination bytes are zero-filled, nothing is read
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 2) conv2d_tf32_kernel(const C2Args a) {
+__global__ void __launch_bounds__(kThreads, 2) conv2d_f16_kernel(const C2Args a) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   unsigned char* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -130,10 +150,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv2d_tf32_kernel(const C2Args a
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t idesc = umma_idesc_tf32(kMT, NT);
+  const uint32_t idesc = umma_idesc_f16(kMT, NT);
 
   // Each thread moves four 16-byte pieces per chunk: piece p = tid + 256 i -> row p >> 3 (= tid/8 + 32 i) of the tile,
-  // 16-byte group p & 7 (= tid & 7: four channels) of the row.  Top-left input coordinate of its four rows:
+  // 16-byte group p & 7 (= tid & 7: eight FP16 channels) of the row.  Top-left input coordinate of its four rows:
   const int grp = tid & 7;
   int ri[4], rj[4];
   uint32_t dst_off[4];
@@ -146,29 +166,29 @@ __global__ void __launch_bounds__(kThreads, 2) conv2d_tf32_kernel(const C2Args a
     rj[i] = 2 * oj - a.pl;
     dst_off[i] = (uint32_t)row * 128u + (uint32_t)((grp ^ (row & 7)) << 4);   // UMMA K-major SWIZZLE_128B
   }
-  const float* hb = a.h1 + (size_t)b * a.H1 * a.W1 * F;
+  const __half* hb = a.h1 + (size_t)b * a.H1 * a.W1 * F;
 
-  // h1 already holds TF32-rounded values: the A operand of a chunk — tap (di, dj), channels [32 cc, 32 cc + 32) of
+  // h1 is FP16: the A operand of a chunk — tap (di, dj), channels [64 cc, 64 cc + 64) of
   // the 128 positions — is gathered with cp.async straight into the swizzled tile (zero-filled outside the image /
   // beyond the last channel), kC2Stages - 1 chunks ahead of the MMAs; nothing passes through registers.
   auto issue_a = [&](int kc) {
     const int tap = kc / a.cpt, cc = kc - tap * a.cpt;
     const int di = tap / 3, dj = tap - 3 * di;
-    const int c = cc * kKC + 4 * grp;
+    const int c = cc * kC2KC + 8 * grp;
     const bool cok = c < F;
     const uint32_t base = sA_u + (uint32_t)(kc % kC2Stages) * kABytes;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = ri[i] + di, q = rj[i] + dj;
       const bool ok = cok && r >= 0 && r < a.H1 && q >= 0 && q < a.W1;
-      const float* src = ok ? hb + ((size_t)r * a.W1 + q) * F + c : hb;
+      const __half* src = ok ? hb + ((size_t)r * a.W1 + q) * F + c : hb;
       cp_async16_zfill(base + dst_off[i], src, ok);
     }
   };
   auto fetch_b = [&](int kc) {
     const int sb = kc % kC2Stages;
     mbar_expect_tx(bar_bfull(sb), bBytes);
-    bulk_g2s(sB_u + sb * bBytes, a.bpack + (size_t)kc * NT * kKC, bBytes, bar_bfull(sb));
+    bulk_g2s(sB_u + sb * bBytes, a.bpack + (size_t)kc * NT * kKC, bBytes, bar_bfull(sb));   // NT*32 floats = NT*64 halves
   };
   for (int kc = 0; kc < kC2Stages - 1; ++kc) {
     if (kc < n_chunks) {
@@ -188,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv2d_tf32_kernel(const C2Args a
       const uint64_t da = umma_desc_sw128(sA_u + s * kABytes);
       const uint64_t db = umma_desc_sw128(sB_u + s * bBytes);
       for (int k = 0; k < 4; ++k)
-        umma_tf32(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+        umma_f16(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
       umma_commit(bar_free(s));
       if (kc == n_chunks - 1) umma_commit(bar_acc);
     }
@@ -248,19 +268,19 @@ __global__ void __launch_bounds__(kThreads, 2) conv2d_tf32_kernel(const C2Args a
 }
 
 // w2 [3,3,F,F] (Keras kernel: tap, c_in, c_out) -> per (tap, chunk) shared-memory image of B: row n (128 bytes) holds
-// input channels c0..c0+31 of filter n, 16-byte groups XOR-swizzled by (n & 7), TF32-rounded; rows n >= F and
-// channels >= F are zero.
-__global__ void pack_w2_kernel(const float* __restrict__ w2, int F, int NT, int cpt, float* __restrict__ out) {
-  const size_t total = (size_t)9 * cpt * NT * kKC;
+// input channels c0..c0+63 of filter n as FP16, 16-byte groups (8 channels) XOR-swizzled by (n & 7); rows n >= F and
+// channels >= F are zero.  `out` is addressed in halves; one chunk image is NT*64 halves = NT*128 bytes.
+__global__ void pack_w2_kernel(const float* __restrict__ w2, int F, int NT, int cpt, __half* __restrict__ out) {
+  const size_t total = (size_t)9 * cpt * NT * kC2KC;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int cl = (int)(i % kKC);
-    const int n = (int)((i / kKC) % NT);
-    const int kc = (int)(i / ((size_t)kKC * NT));
-    const int tap = kc / cpt, c = (kc - tap * cpt) * kKC + cl;
+    const int cl = (int)(i % kC2KC);
+    const int n = (int)((i / kC2KC) % NT);
+    const int kc = (int)(i / ((size_t)kC2KC * NT));
+    const int tap = kc / cpt, c = (kc - tap * cpt) * kC2KC + cl;
     const float v = (c < F && n < F) ? w2[((size_t)tap * F + c) * F + n] : 0.0f;
-    const size_t base = (size_t)kc * NT * kKC;
-    const int phys = n * kKC + ((((cl >> 2) ^ (n & 7)) << 2) | (cl & 3));
-    out[base + phys] = __uint_as_float(to_tf32(v));
+    const size_t base = (size_t)kc * NT * kC2KC;
+    const int phys = n * kC2KC + ((((cl >> 3) ^ (n & 7)) << 3) | (cl & 7));
+    out[base + phys] = __float2half_rn(v);
   }
 }
 
@@ -279,16 +299,16 @@ extern "C" int tasr_conv2d_plan_create(const float* w1, const float* b1, const f
                                        TasrConv2dPlan** out, tasr_stream_t stream) {
   if (!w1 || !b1 || !w2 || !b2 || !out) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_plan_create: null argument");
   *out = nullptr;
-  if (filters < 4 || (filters & 3) || filters > 256)
-    return fail(TASR_ERR_UNSUPPORTED, "tasr_conv2d_plan_create: filters=%d must be a multiple of 4 in [4,256]", filters);
+  if (filters < 8 || (filters & 7) || filters > 256)
+    return fail(TASR_ERR_UNSUPPORTED, "tasr_conv2d_plan_create: filters=%d must be a multiple of 8 in [8,256]", filters);
   TasrConv2dPlan* p = new TasrConv2dPlan();
   p->filters = filters;
   p->NT = (filters + 31) & ~31;
-  p->cpt = (filters + kKC - 1) / kKC;
+  p->cpt = (filters + kC2KC - 1) / kC2KC;
   p->d_w1 = p->d_b1 = p->d_b2 = p->d_bpack = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = check_cuda(cudaGetDevice(&p->device), "cudaGetDevice");
-  const size_t nb = (size_t)9 * p->cpt * p->NT * kKC;
+  const size_t nb = (size_t)9 * p->cpt * p->NT * kKC;   // in floats (= NT*64 halves per chunk)
   if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_w1, (size_t)9 * filters * sizeof(float)), "cudaMalloc conv1 taps");
   if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_b1, (size_t)filters * sizeof(float)), "cudaMalloc conv1 bias");
   if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_b2, (size_t)p->NT * sizeof(float)), "cudaMalloc conv2 bias");
@@ -298,13 +318,14 @@ extern "C" int tasr_conv2d_plan_create(const float* w1, const float* b1, const f
   if (rc == TASR_OK) rc = check_cuda(cudaMemsetAsync(p->d_b2, 0, (size_t)p->NT * sizeof(float), st), "clear conv2 bias");
   if (rc == TASR_OK) rc = check_cuda(cudaMemcpyAsync(p->d_b2, b2, (size_t)filters * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy conv2 bias");
   if (rc == TASR_OK) {
-    pack_w2_kernel<<<(unsigned)((nb + 255) / 256 > 1024 ? 1024 : (nb + 255) / 256), 256, 0, st>>>(w2, filters, p->NT, p->cpt, p->d_bpack);
+    pack_w2_kernel<<<(unsigned)((2 * nb + 255) / 256 > 1024 ? 1024 : (2 * nb + 255) / 256), 256, 0, st>>>(
+        w2, filters, p->NT, p->cpt, reinterpret_cast<__half*>(p->d_bpack));
     count_launch();
     rc = check_cuda(cudaGetLastError(), "pack_w2_kernel");
   }
   if (rc == TASR_OK)
-    rc = check_cuda(cudaFuncSetAttribute(conv2d_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes(256)),
-                    "cudaFuncSetAttribute(conv2d_tf32_kernel)");
+    rc = check_cuda(cudaFuncSetAttribute(conv2d_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes(256)),
+                    "cudaFuncSetAttribute(conv2d_f16_kernel)");
   if (rc != TASR_OK) { tasr_conv2d_plan_destroy(p); return rc; }
   *out = p;
   return TASR_OK;
@@ -325,16 +346,16 @@ extern "C" int tasr_conv2d_output_shape(int32_t t, int32_t w, int32_t* h1, int32
   return TASR_OK;
 }
 
-extern "C" int tasr_conv2d_subsample_tf32(const TasrConv2dPlan* p, const float* feat, int32_t B, int32_t T, int32_t W,
-                                          float* h1, float* out, tasr_stream_t stream) {
-  if (!p || !feat || !h1 || !out) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample_tf32: null argument");
-  if (B < 0 || T < 0 || W < 0) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample_tf32: negative size");
-  if (!aligned16(h1) || !aligned16(out)) return fail(TASR_ERR_MISALIGNED, "tasr_conv2d_subsample_tf32: h1/out must be 16-byte aligned");
+extern "C" int tasr_conv2d_subsample(const TasrConv2dPlan* p, const float* feat, int32_t B, int32_t T, int32_t W,
+                                          void* h1, float* out, tasr_stream_t stream) {
+  if (!p || !feat || !h1 || !out) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample: null argument");
+  if (B < 0 || T < 0 || W < 0) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample: negative size");
+  if (!aligned16(h1) || !aligned16(out)) return fail(TASR_ERR_MISALIGNED, "tasr_conv2d_subsample: h1/out must be 16-byte aligned");
   int dev = 0;
   TASR_CUDA(cudaGetDevice(&dev));
-  if (dev != p->device) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample_tf32: plan was created on device %d, current device is %d", p->device, dev);
+  if (dev != p->device) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample: plan was created on device %d, current device is %d", p->device, dev);
   if (B == 0 || T == 0 || W == 0) return TASR_OK;
-  if (B > 65535) return fail(TASR_ERR_UNSUPPORTED, "tasr_conv2d_subsample_tf32: batch > 65535");
+  if (B > 65535) return fail(TASR_ERR_UNSUPPORTED, "tasr_conv2d_subsample: batch > 65535");
   cudaStream_t st = (cudaStream_t)stream;
   const int F = p->filters;
   int H1, W1, H2, W2, pt1, pl1, pt2, pl2;
@@ -343,16 +364,16 @@ extern "C" int tasr_conv2d_subsample_tf32(const TasrConv2dPlan* p, const float* 
   {
     dim3 grid1((H1 + kC1Rows - 1) / kC1Rows, B);
     const size_t smem1 = (size_t)(2 * kC1Rows + 1) * (2 * W1 + 1) * sizeof(float);
-    if (smem1 > 48 * 1024) return fail(TASR_ERR_UNSUPPORTED, "tasr_conv2d_subsample_tf32: feature width %d too large", W);
-    conv2d_first_kernel<<<grid1, 8 * (F / 4), smem1, st>>>(feat, p->d_w1, p->d_b1, h1, T, W, H1, W1, F, pt1, pl1);
+    if (smem1 > 48 * 1024) return fail(TASR_ERR_UNSUPPORTED, "tasr_conv2d_subsample: feature width %d too large", W);
+    conv2d_first_kernel<<<grid1, 8 * (F / 4), smem1, st>>>(feat, p->d_w1, p->d_b1, reinterpret_cast<__half*>(h1), T, W, H1, W1, F, pt1, pl1);
     TASR_LAUNCH_CHECK("conv2d_first_kernel");
   }
   C2Args a;
-  a.h1 = h1; a.bpack = p->d_bpack; a.bias = p->d_b2; a.y = out;
+  a.h1 = reinterpret_cast<const __half*>(h1); a.bpack = p->d_bpack; a.bias = p->d_b2; a.y = out;
   a.H1 = H1; a.W1 = W1; a.H2 = H2; a.W2 = W2; a.F = F; a.NT = p->NT; a.cpt = p->cpt; a.pt = pt2; a.pl = pl2;
   const int M_total = H2 * W2;
   dim3 grid((M_total + kMT - 1) / kMT, 1, B);
-  conv2d_tf32_kernel<<<grid, kThreads, c2_smem_bytes(p->NT), st>>>(a);
-  TASR_LAUNCH_CHECK("conv2d_tf32_kernel");
+  conv2d_f16_kernel<<<grid, kThreads, c2_smem_bytes(p->NT), st>>>(a);
+  TASR_LAUNCH_CHECK("conv2d_f16_kernel");
   return TASR_OK;
 }
