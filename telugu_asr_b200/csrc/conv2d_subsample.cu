@@ -49,7 +49,8 @@ struct C2Args {
 // shared memory with a zero border (no bounds tests in the loop); thread <-> (one of 8 positions, 4 consecutive
 // filters), its nine float4 tap weights and bias live in registers for the whole block.
 constexpr int kC1Rows = 8;
-__global__ void __launch_bounds__(512) conv2d_first_kernel(const float* __restrict__ x, const float* __restrict__ w1,
+template <int MAXT, int MINB>   // (288, 3) for filters <= 144: 72 registers, three blocks per SM; (512, 1) otherwise
+__global__ void __launch_bounds__(MAXT, MINB) conv2d_first_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                             const float* __restrict__ b1, __half* __restrict__ h1,
                                                             int T, int W, int H1, int W1, int F, int pt, int pl) {
   extern __shared__ float xs[];                      // [2*kC1Rows+1][SW], SW = 2*W1+1 columns starting at column -pl
@@ -365,7 +366,10 @@ extern "C" int tasr_conv2d_subsample(const TasrConv2dPlan* p, const float* feat,
     dim3 grid1((H1 + kC1Rows - 1) / kC1Rows, B);
     const size_t smem1 = (size_t)(2 * kC1Rows + 1) * (2 * W1 + 1) * sizeof(float);
     if (smem1 > 48 * 1024) return fail(TASR_ERR_UNSUPPORTED, "tasr_conv2d_subsample: feature width %d too large", W);
-    conv2d_first_kernel<<<grid1, 8 * (F / 4), smem1, st>>>(feat, p->d_w1, p->d_b1, reinterpret_cast<__half*>(h1), T, W, H1, W1, F, pt1, pl1);
+    if (8 * (F / 4) <= 288)
+      conv2d_first_kernel<288, 3><<<grid1, 8 * (F / 4), smem1, st>>>(feat, p->d_w1, p->d_b1, reinterpret_cast<__half*>(h1), T, W, H1, W1, F, pt1, pl1);
+    else
+      conv2d_first_kernel<512, 1><<<grid1, 8 * (F / 4), smem1, st>>>(feat, p->d_w1, p->d_b1, reinterpret_cast<__half*>(h1), T, W, H1, W1, F, pt1, pl1);
     TASR_LAUNCH_CHECK("conv2d_first_kernel");
   }
   C2Args a;
