@@ -240,6 +240,18 @@ int tasr_conv2d_output_shape(int32_t t, int32_t w, int32_t* h1, int32_t* w1, int
 int tasr_conv2d_subsample(const TasrConv2dPlan* plan, const float* feat, int32_t batch, int32_t t, int32_t w,
                                void* h1_workspace, float* out, tasr_stream_t stream);
 
+/* Ragged form for zero-padded batches (src/dataset.py:236-252 pads the features with 0.0 and the reference convolves the
+ * padding too): n_frames [batch] (device int32) says that feature rows t >= n_frames[b] are zero — they are then never
+ * read, so the features may be a lean tensor.  An output row whose whole receptive field is padding repeats one
+ * [w2, filters] pattern (the bottom border row excepted); tasr_conv2d_plan_prepare_ragged computes that pattern for
+ * feature width w with these very kernels on a zero input (synchronises the stream; call once per width, outside any
+ * graph capture), and tasr_conv2d_subsample_ragged fills the 128-position tiles that consist only of such rows instead
+ * of computing them, and skips the first-layer rows nobody reads.  Every value of `out` is bit-identical to
+ * tasr_conv2d_subsample on the same (zero-padded) input. */
+int tasr_conv2d_plan_prepare_ragged(TasrConv2dPlan* plan, int32_t w, tasr_stream_t stream);
+int tasr_conv2d_subsample_ragged(const TasrConv2dPlan* plan, const float* feat, const int32_t* n_frames, int32_t batch,
+                                 int32_t t, int32_t w, void* h1_workspace, float* out, tasr_stream_t stream);
+
 /* SpecAugment, deterministic half (replaces FreqMasking.augment / TimeMasking.augment,
  * src/augmentations/specaugment.py:6-62, applied per utterance at src/dataset.py:172): in place on
  * feat [batch, t_max, f]: feat[b,t,:] *= 0 for t in [t0, t0+t) of every time mask, feat[b,:,k] *= 0 for

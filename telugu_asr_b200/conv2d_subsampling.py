@@ -23,7 +23,7 @@ __all__ = ["Conv2dSubsampling"]
 class Conv2dSubsampling:
     def __init__(self, subsampling_config: dict | None = None, kernel_regularizer=None, bias_regularizer=None,
                  kernel_initializer=None, bias_initializer=None, name: str = "Conv2dSubsampling", seed: int | None = None,
-                 **kwargs):
+                 assume_zero_padding: bool = True, **kwargs):
         subsampling_config = subsampling_config or {}
         self.name = name
         self.filter = int(subsampling_config.get("filters", 128))          # encoder.py:22
@@ -34,6 +34,10 @@ class Conv2dSubsampling:
             raise NotImplementedError("Conv2dSubsampling kernels are built for kernel_size=3, strides=2, padding='same' "
                                       "(config/conformer.yaml:22-27)")
         self._seed = seed
+        # ragged mode: feature rows t >= outputs_length[b] are taken to be the collate's 0.0 padding (src/dataset.py:241);
+        # tiles deep inside the padding are filled with the pattern the convolutions produce there.  Same values everywhere.
+        self.assume_zero_padding = bool(assume_zero_padding)
+        self._ragged_w = None
         self.weights = None       # [(w1 [3,3,1,F], b1 [F]), (w2 [3,3,F,F], b2 [F])] on the device
         self._plan = None
         self._device = None
@@ -64,6 +68,7 @@ class Conv2dSubsampling:
         if len(out) != 2:
             raise ValueError("expected weights for two Conv2D layers")
         self._destroy_plan()
+        self._ragged_w = None
         self.weights = out
         self._device = device
 
@@ -120,10 +125,19 @@ class Conv2dSubsampling:
         L = _native.lib()
         with torch.cuda.device(x.device):
             st = _native.stream_ptr()
-            _native.check(L.tasr_conv2d_subsample(self._plan, x.data_ptr(), B, T, W, work.data_ptr(), out.data_ptr(), st))
-            out_len = None
+            ln = None
             if outputs_length is not None:
                 ln = _native.require_cuda(outputs_length, "outputs_length").to(torch.int32).contiguous()
+            if ln is not None and self.assume_zero_padding and B and T:
+                if self._ragged_w != W:        # once per feature width (synchronises; not inside a graph capture)
+                    _native.check(L.tasr_conv2d_plan_prepare_ragged(self._plan, W, st))
+                    self._ragged_w = W
+                _native.check(L.tasr_conv2d_subsample_ragged(self._plan, x.data_ptr(), ln.data_ptr(), B, T, W,
+                                                             work.data_ptr(), out.data_ptr(), st))
+            else:
+                _native.check(L.tasr_conv2d_subsample(self._plan, x.data_ptr(), B, T, W, work.data_ptr(), out.data_ptr(), st))
+            out_len = None
+            if ln is not None:
                 out_len = torch.empty((1, ln.numel()), dtype=torch.int32, device=x.device)
                 if ln.numel():
                     k, s, same = (C.c_int32 * 1)(3), (C.c_int32 * 1)(2), (C.c_int32 * 1)(1)

@@ -33,6 +33,10 @@ struct TasrConv2dPlan {
   float* d_b1;          // [F]
   float* d_b2;          // [NT] zero padded
   float* d_bpack;       // [9*cpt][NT*64 halves = NT*32 floats] shared-memory images of the second-layer weights (FP16)
+  // ragged mode: what the layer outputs on a row whose whole receptive field is collate padding (zero features), for
+  // input width pat_w: [W2][F] floats, computed by these very kernels on a zero input (tasr_conv2d_plan_prepare_ragged)
+  float* d_pattern;
+  int pat_w;
 };
 
 namespace {
@@ -43,7 +47,17 @@ struct C2Args {
   const float* bias;
   float* y;
   int32_t H1, W1, H2, W2, F, NT, cpt, pt, pl;
+  // ragged mode (n_frames != nullptr): feature rows t >= n_frames[b] are zero.  Output rows whose receptive field lies
+  // entirely there (and not on the bottom border) equal `pattern` [W2][F]: tiles made only of such rows are filled.
+  const int32_t* n_frames;
+  const float* pattern;
+  int32_t pt1;
 };
+
+// First h1 row / output row that no longer depends on the data of an utterance with n valid feature rows.
+__device__ __forceinline__ int c2_first_const_h1(int n, int pt1) { return (max(n, 0) + pt1 + 1) >> 1; }          // ceil((n+pt1)/2)
+__device__ __forceinline__ int c2_first_const_out(int c1, int pt2) { return (c1 + pt2 + 1) >> 1; }               // ceil((c1+pt2)/2)
+
 
 // conv1: one block = kC1Rows output rows of one utterance.  The 2*kC1Rows+1 input rows it needs are staged once in
 // shared memory with a zero border (no bounds tests in the loop); thread <-> (one of 8 positions, 4 consecutive
@@ -52,16 +66,29 @@ constexpr int kC1Rows = 8;
 template <int MAXT, int MINB>   // (288, 3) for filters <= 144: 72 registers, three blocks per SM; (512, 1) otherwise
 __global__ void __launch_bounds__(MAXT, MINB) conv2d_first_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                             const float* __restrict__ b1, __half* __restrict__ h1,
-                                                            int T, int W, int H1, int W1, int F, int pt, int pl) {
+                                                            int T, int W, int H1, int W1, int F, int pt, int pl,
+                                                            const int32_t* __restrict__ n_frames, int pt2, int H2, int rows_per_tile) {
   extern __shared__ float xs[];                      // [2*kC1Rows+1][SW], SW = 2*W1+1 columns starting at column -pl
   const int SW = 2 * W1 + 1;
   const int b = blockIdx.y, i0 = blockIdx.x * kC1Rows;
   const int nrows = min(kC1Rows, H1 - i0);
+  int n_valid = T;
+  if (n_frames != nullptr) {
+    // Ragged: the second kernel computes only tiles that hold a data-dependent output row (i' < c2) or the bottom
+    // border row; it therefore reads h1 rows below 2*(c2 + rows_per_tile) + 2 and the last 2*rows_per_tile + 3 rows.
+    // Blocks outside both ranges write nothing.  Rows past the data are computed from zeros WITHOUT reading the
+    // features there (they may be a lean tensor's unwritten rows).
+    n_valid = min(max(n_frames[b], 0), T);
+    const int c2 = c2_first_const_out(c2_first_const_h1(n_valid, pt), pt2);
+    const int head_end = 2 * (c2 + rows_per_tile) + 2;
+    const int tail_begin = 2 * (H2 - 1 - rows_per_tile) - pt2;
+    if (i0 >= head_end && i0 + nrows <= tail_begin) return;
+  }
   const float* xb = x + (size_t)b * T * W;
   for (int k = threadIdx.x; k < (2 * kC1Rows + 1) * SW; k += blockDim.x) {
     const int d = k / SW, cc = k - d * SW;
     const int r = 2 * i0 + d - pt, c = cc - pl;
-    xs[k] = (r >= 0 && r < T && c >= 0 && c < W) ? __ldg(xb + (size_t)r * W + c) : 0.0f;
+    xs[k] = (r >= 0 && r < n_valid && c >= 0 && c < W) ? __ldg(xb + (size_t)r * W + c) : 0.0f;
   }
   const int f4n = F >> 2;
   const int f = (threadIdx.x % f4n) * 4, p0 = threadIdx.x / f4n;
@@ -140,6 +167,22 @@ __global__ void __launch_bounds__(kThreads, 2) conv2d_f16_kernel(const C2Args a)
   const int b = blockIdx.z, t0 = blockIdx.x * kMT;
   const int M_total = a.H2 * a.W2;
   const int n_chunks = 9 * a.cpt;
+
+  if (a.n_frames != nullptr) {           // CTA-uniform: a tile made only of constant rows is filled, not computed
+    const int n = min(max(a.n_frames[b], 0), 0x3fffffff);
+    const int c2 = c2_first_const_out(c2_first_const_h1(n, a.pt1), a.pt);
+    const int m_hi = min(t0 + kMT, M_total) - 1;
+    if (t0 / a.W2 >= c2 && m_hi / a.W2 < a.H2 - 1) {
+      const int q4 = F >> 2;
+      for (int idx = tid; idx < (m_hi - t0 + 1) * q4; idx += kThreads) {
+        const int row = idx / q4, c4 = idx - row * q4;
+        const int m = t0 + row;
+        const float4 pv = __ldg(reinterpret_cast<const float4*>(a.pattern + (size_t)(m % a.W2) * F) + c4);
+        *reinterpret_cast<float4*>(a.y + ((size_t)b * M_total + m) * F + 4 * c4) = pv;
+      }
+      return;
+    }
+  }
 
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   if (tid == 32) {
@@ -307,6 +350,8 @@ extern "C" int tasr_conv2d_plan_create(const float* w1, const float* b1, const f
   p->NT = (filters + 31) & ~31;
   p->cpt = (filters + kC2KC - 1) / kC2KC;
   p->d_w1 = p->d_b1 = p->d_b2 = p->d_bpack = nullptr;
+  p->d_pattern = nullptr;
+  p->pat_w = 0;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = check_cuda(cudaGetDevice(&p->device), "cudaGetDevice");
   const size_t nb = (size_t)9 * p->cpt * p->NT * kKC;   // in floats (= NT*64 halves per chunk)
@@ -334,7 +379,7 @@ extern "C" int tasr_conv2d_plan_create(const float* w1, const float* b1, const f
 
 extern "C" int tasr_conv2d_plan_destroy(TasrConv2dPlan* p) {
   if (!p) return TASR_OK;
-  cudaFree(p->d_w1); cudaFree(p->d_b1); cudaFree(p->d_b2); cudaFree(p->d_bpack);
+  cudaFree(p->d_w1); cudaFree(p->d_b1); cudaFree(p->d_b2); cudaFree(p->d_bpack); cudaFree(p->d_pattern);
   delete p;
   return TASR_OK;
 }
@@ -347,37 +392,83 @@ extern "C" int tasr_conv2d_output_shape(int32_t t, int32_t w, int32_t* h1, int32
   return TASR_OK;
 }
 
-extern "C" int tasr_conv2d_subsample(const TasrConv2dPlan* p, const float* feat, int32_t B, int32_t T, int32_t W,
-                                          void* h1, float* out, tasr_stream_t stream) {
-  if (!p || !feat || !h1 || !out) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample: null argument");
-  if (B < 0 || T < 0 || W < 0) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample: negative size");
-  if (!aligned16(h1) || !aligned16(out)) return fail(TASR_ERR_MISALIGNED, "tasr_conv2d_subsample: h1/out must be 16-byte aligned");
+static int conv2d_launch(const char* who, const TasrConv2dPlan* p, const float* feat, const int32_t* n_frames, int32_t B,
+                         int32_t T, int32_t W, void* h1, float* out, tasr_stream_t stream) {
+  if (!p || !feat || !h1 || !out) return fail(TASR_ERR_BAD_ARG, "%s: null argument", who);
+  if (B < 0 || T < 0 || W < 0) return fail(TASR_ERR_BAD_ARG, "%s: negative size", who);
+  if (!aligned16(h1) || !aligned16(out)) return fail(TASR_ERR_MISALIGNED, "%s: h1/out must be 16-byte aligned", who);
   int dev = 0;
   TASR_CUDA(cudaGetDevice(&dev));
-  if (dev != p->device) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample: plan was created on device %d, current device is %d", p->device, dev);
+  if (dev != p->device) return fail(TASR_ERR_BAD_ARG, "%s: plan was created on device %d, current device is %d", who, p->device, dev);
   if (B == 0 || T == 0 || W == 0) return TASR_OK;
-  if (B > 65535) return fail(TASR_ERR_UNSUPPORTED, "tasr_conv2d_subsample: batch > 65535");
+  if (B > 65535) return fail(TASR_ERR_UNSUPPORTED, "%s: batch > 65535", who);
   cudaStream_t st = (cudaStream_t)stream;
   const int F = p->filters;
   int H1, W1, H2, W2, pt1, pl1, pt2, pl2;
   same_pads(T, 3, 2, &H1, &pt1); same_pads(W, 3, 2, &W1, &pl1);
   same_pads(H1, 3, 2, &H2, &pt2); same_pads(W1, 3, 2, &W2, &pl2);
+  if (n_frames && (p->pat_w != W || !p->d_pattern))
+    return fail(TASR_ERR_BAD_ARG, "%s: call tasr_conv2d_plan_prepare_ragged for feature width %d first", who, W);
+  const int rows_per_tile = (kMT + W2 - 1) / W2 + 1;   // output rows a 128-position tile can touch
   {
     dim3 grid1((H1 + kC1Rows - 1) / kC1Rows, B);
     const size_t smem1 = (size_t)(2 * kC1Rows + 1) * (2 * W1 + 1) * sizeof(float);
-    if (smem1 > 48 * 1024) return fail(TASR_ERR_UNSUPPORTED, "tasr_conv2d_subsample: feature width %d too large", W);
+    if (smem1 > 48 * 1024) return fail(TASR_ERR_UNSUPPORTED, "%s: feature width %d too large", who, W);
     if (8 * (F / 4) <= 288)
-      conv2d_first_kernel<288, 3><<<grid1, 8 * (F / 4), smem1, st>>>(feat, p->d_w1, p->d_b1, reinterpret_cast<__half*>(h1), T, W, H1, W1, F, pt1, pl1);
+      conv2d_first_kernel<288, 3><<<grid1, 8 * (F / 4), smem1, st>>>(feat, p->d_w1, p->d_b1, reinterpret_cast<__half*>(h1), T, W, H1, W1,
+                                                                     F, pt1, pl1, n_frames, pt2, H2, rows_per_tile);
     else
-      conv2d_first_kernel<512, 1><<<grid1, 8 * (F / 4), smem1, st>>>(feat, p->d_w1, p->d_b1, reinterpret_cast<__half*>(h1), T, W, H1, W1, F, pt1, pl1);
+      conv2d_first_kernel<512, 1><<<grid1, 8 * (F / 4), smem1, st>>>(feat, p->d_w1, p->d_b1, reinterpret_cast<__half*>(h1), T, W, H1, W1,
+                                                                     F, pt1, pl1, n_frames, pt2, H2, rows_per_tile);
     TASR_LAUNCH_CHECK("conv2d_first_kernel");
   }
   C2Args a;
   a.h1 = reinterpret_cast<const __half*>(h1); a.bpack = p->d_bpack; a.bias = p->d_b2; a.y = out;
   a.H1 = H1; a.W1 = W1; a.H2 = H2; a.W2 = W2; a.F = F; a.NT = p->NT; a.cpt = p->cpt; a.pt = pt2; a.pl = pl2;
+  a.n_frames = n_frames; a.pattern = p->d_pattern; a.pt1 = pt1;
   const int M_total = H2 * W2;
   dim3 grid((M_total + kMT - 1) / kMT, 1, B);
   conv2d_f16_kernel<<<grid, kThreads, c2_smem_bytes(p->NT), st>>>(a);
   TASR_LAUNCH_CHECK("conv2d_f16_kernel");
   return TASR_OK;
+}
+
+extern "C" int tasr_conv2d_subsample(const TasrConv2dPlan* p, const float* feat, int32_t B, int32_t T, int32_t W,
+                                     void* h1, float* out, tasr_stream_t stream) {
+  return conv2d_launch("tasr_conv2d_subsample", p, feat, nullptr, B, T, W, h1, out, stream);
+}
+
+extern "C" int tasr_conv2d_plan_prepare_ragged(TasrConv2dPlan* p, int32_t W, tasr_stream_t stream) {
+  if (!p || W <= 0) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_plan_prepare_ragged: bad argument");
+  if (p->pat_w == W && p->d_pattern) return TASR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int F = p->filters, T = 32;                      // zero input tall enough that output row 1 sees no border
+  int H1, W1, H2, W2, pb;
+  same_pads(T, 3, 2, &H1, &pb); same_pads(W, 3, 2, &W1, &pb);
+  same_pads(H1, 3, 2, &H2, &pb); same_pads(W1, 3, 2, &W2, &pb);
+  float *zero = nullptr, *out = nullptr;
+  void* h1 = nullptr;
+  int rc = check_cuda(cudaMalloc(&zero, (size_t)T * W * sizeof(float)), "cudaMalloc");
+  if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&h1, (size_t)H1 * W1 * F * 2), "cudaMalloc");
+  if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&out, (size_t)H2 * W2 * F * sizeof(float)), "cudaMalloc");
+  if (rc == TASR_OK) rc = check_cuda(cudaMemsetAsync(zero, 0, (size_t)T * W * sizeof(float), st), "cudaMemsetAsync");
+  if (rc == TASR_OK) rc = conv2d_launch("tasr_conv2d_plan_prepare_ragged", p, zero, nullptr, 1, T, W, h1, out, stream);
+  if (rc == TASR_OK) {
+    cudaFree(p->d_pattern);
+    p->d_pattern = nullptr;
+    rc = check_cuda(cudaMalloc(&p->d_pattern, (size_t)W2 * F * sizeof(float)), "cudaMalloc pattern");
+  }
+  // output row 1 of the zero input: every tap inside the image, every h1 value the constant relu(b1)
+  if (rc == TASR_OK) rc = check_cuda(cudaMemcpyAsync(p->d_pattern, out + (size_t)1 * W2 * F, (size_t)W2 * F * sizeof(float),
+                                                     cudaMemcpyDeviceToDevice, st), "copy pattern");
+  if (rc == TASR_OK) rc = check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+  cudaFree(zero); cudaFree(h1); cudaFree(out);
+  if (rc == TASR_OK) p->pat_w = W;
+  return rc;
+}
+
+extern "C" int tasr_conv2d_subsample_ragged(const TasrConv2dPlan* p, const float* feat, const int32_t* n_frames, int32_t B,
+                                            int32_t T, int32_t W, void* h1, float* out, tasr_stream_t stream) {
+  if (!n_frames) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample_ragged: null n_frames");
+  return conv2d_launch("tasr_conv2d_subsample_ragged", p, feat, n_frames, B, T, W, h1, out, stream);
 }

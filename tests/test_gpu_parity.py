@@ -939,3 +939,35 @@ def test_conv2d_subsampling_matches_oracle(cuda_device, T, B, filters):
         tasr.Conv2dSubsampling({"filters": 144, "kernel_size": 5})
     with pytest.raises(ValueError):
         layer.set_weights([(ws[0][0][:2], ws[0][1]), ws[1]], cuda_device)
+
+
+@pytest.mark.parametrize("T", [1498, 1497, 203])
+def test_conv2d_subsampling_ragged_is_bit_identical_to_dense(cuda_device, T):
+    """Ragged mode fills the tiles that lie in the collate padding with the pattern the two convolutions produce
+    there and skips the first-layer rows nobody reads: every output value must equal the dense run bit for bit —
+    with the workspace and outputs NaN-poisoned (nothing unwritten is read) and the features beyond each length
+    replaced by NaN for the ragged call (they are declared zero and must not be touched)."""
+    B = 10
+    rng = np.random.default_rng(T)
+    lens = np.array([T, 0, 1, 2, 3, 100, T // 2, T - 1, T - 7, 640], dtype=np.int32)
+    lens = np.minimum(lens, T)
+    x = rng.standard_normal((B, T, 80, 1)).astype(np.float32)
+    for b in range(B):
+        x[b, lens[b]:] = 0.0
+    x_nan = x.copy()
+    for b in range(B):
+        x_nan[b, lens[b]:] = np.nan
+    ws = oracle.glorot_conv2d_weights(144, seed=9)
+    res = {}
+    for ragged in (False, True):
+        layer = tasr.Conv2dSubsampling({"filters": 144, "kernel_size": 3, "strides": 2, "padding": "same"}, assume_zero_padding=ragged)
+        layer.set_weights(ws, cuda_device)
+        _native.poison_allocations = True
+        try:
+            res[ragged] = _call_or_skip(layer, [gpu(x_nan if ragged else x, cuda_device), gpu(lens, cuda_device)])
+            torch.cuda.synchronize()
+        finally:
+            _native.poison_allocations = False
+    assert torch.equal(res[True][1], res[False][1])
+    assert not torch.isnan(res[True][0]).any()
+    assert torch.equal(res[True][0], res[False][0])
