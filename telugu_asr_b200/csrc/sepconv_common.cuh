@@ -143,6 +143,54 @@ __device__ __forceinline__ float gelu_erf_fast(float z) {
   return fmaxf(z, 0.0f) - fabsf(t);
 }
 
+// ---- packed FP32x2 arithmetic (sm_100a FADD2 / FMUL2 / FFMA2): one issue slot for two IEEE-identical operations.
+// The epilogues are bound by instruction issue, not by the FMA pipe, so the bias add and the GELU polynomial of two
+// neighbouring columns share their instructions; every result bit equals the scalar form above.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// bias add + activation of two neighbouring accumulator columns: (acc0 + b0, acc1 + b1) -> act.
+template <int ACT>
+__device__ __forceinline__ void act_apply2(float acc0, float acc1, float b0, float b1, float& o0, float& o1);
+
+__device__ __forceinline__ void gelu_erf_fast2(u64 z2, float& o0, float& o1) {
+  float z0, z1;
+  unpack2(z2, z0, z1);
+  const u64 a2 = pack2(fabsf(z0), fabsf(z1));
+  u64 q = fma2(pack2(-4.732913936e-04f, -4.732913936e-04f), a2, pack2(7.084427742e-03f, 7.084427742e-03f));
+  q = fma2(q, a2, pack2(-5.182704213e-02f, -5.182704213e-02f));
+  q = fma2(q, a2, pack2(-4.599928375e-01f, -4.599928375e-01f));
+  q = fma2(q, a2, pack2(-1.150787652e+00f, -1.150787652e+00f));
+  q = fma2(q, a2, pack2(-3.765495672e-05f, -3.765495672e-05f));
+  float q0, q1;
+  unpack2(q, q0, q1);
+  const u64 t2 = mul2(mul2(pack2(0.5f, 0.5f), z2), pack2(ex2_approx(q0), ex2_approx(q1)));
+  float t0, t1;
+  unpack2(t2, t0, t1);
+  o0 = fmaxf(z0, 0.0f) - fabsf(t0);
+  o1 = fmaxf(z1, 0.0f) - fabsf(t1);
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_apply(float z);
+
+template <int ACT>
+__device__ __forceinline__ void act_apply2(float acc0, float acc1, float b0, float b1, float& o0, float& o1) {
+  const u64 z2 = add2(pack2(acc0, acc1), pack2(b0, b1));
+  if (ACT == TASR_ACT_GELU_ERF) {
+    gelu_erf_fast2(z2, o0, o1);
+  } else {
+    float z0, z1;
+    unpack2(z2, z0, z1);
+    o0 = act_apply<ACT>(z0);
+    o1 = act_apply<ACT>(z1);
+  }
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_apply(float z) {
   if (ACT == TASR_ACT_TANH) return tanh_fast(z);

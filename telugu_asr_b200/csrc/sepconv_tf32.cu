@@ -199,10 +199,8 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
       for (int i = 0; i < 8; ++i) {
         const float4 bv = *reinterpret_cast<const float4*>(sBias + g * 32 + 4 * i);
         float4 o;
-        o.x = act_apply<ACT>(__uint_as_float(r[4 * i + 0]) + bv.x);
-        o.y = act_apply<ACT>(__uint_as_float(r[4 * i + 1]) + bv.y);
-        o.z = act_apply<ACT>(__uint_as_float(r[4 * i + 2]) + bv.z);
-        o.w = act_apply<ACT>(__uint_as_float(r[4 * i + 3]) + bv.w);
+        act_apply2<ACT>(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1]), bv.x, bv.y, o.x, o.y);
+        act_apply2<ACT>(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]), bv.z, bv.w, o.z, o.w);
         *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * i) = o;
       }
       __syncwarp();

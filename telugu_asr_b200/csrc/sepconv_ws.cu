@@ -328,10 +328,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const __grid_
         for (int i = 0; i < 8; ++i) {
           const float4 bv = *reinterpret_cast<const float4*>(sBias + n0 + g * 32 + 4 * i);
           float4 o;
-          o.x = act_apply<ACT>(__uint_as_float(r[4 * i + 0]) + bv.x);
-          o.y = act_apply<ACT>(__uint_as_float(r[4 * i + 1]) + bv.y);
-          o.z = act_apply<ACT>(__uint_as_float(r[4 * i + 2]) + bv.z);
-          o.w = act_apply<ACT>(__uint_as_float(r[4 * i + 3]) + bv.w);
+          act_apply2<ACT>(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1]), bv.x, bv.y, o.x, o.y);
+          act_apply2<ACT>(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]), bv.z, bv.w, o.z, o.w);
           *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * i) = o;
         }
         __syncwarp();
