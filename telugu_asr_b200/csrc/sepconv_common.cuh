@@ -153,6 +153,21 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0,
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
+// Depthwise run of 16 output frames from a 39-row register window (stride 2, 9 taps): outputs j and j + 8 share their
+// nine FMAs as packed FP32x2 instructions (taps ascending, like the scalar loop: identical bits).
+__device__ __forceinline__ void depthwise_run16(const float (&v)[39], const float (&w)[9], float (&acc)[16]) {
+  u64 wp[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wp[k] = pack2(w[k], w[k]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    u64 a2 = pack2(0.0f, 0.0f);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a2 = fma2(pack2(v[2 * j + k], v[2 * j + 16 + k]), wp[k], a2);
+    unpack2(a2, acc[j], acc[j + 8]);
+  }
+}
+
 // bias add + activation of two neighbouring accumulator columns: (acc0 + b0, acc1 + b1) -> act.
 template <int ACT>
 __device__ __forceinline__ void act_apply2(float acc0, float acc1, float b0, float b1, float& o0, float& o1);

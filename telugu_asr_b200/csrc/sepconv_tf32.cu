@@ -159,14 +159,13 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
     }
     if (run_needed) {
     unsigned char* As = sA + s * kABytes;
+    float acc[kRun];
+    depthwise_run16(v, w, acc);
 #pragma unroll
     for (int j = 0; j < kRun; ++j) {
-      float acc = 0.0f;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) acc = fmaf(v[2 * j + k], w[k], acc);
       const int row = warp * kRun + j;
       const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u;
-      *reinterpret_cast<uint32_t*>(As + off) = to_tf32(acc);
+      *reinterpret_cast<uint32_t*>(As + off) = to_tf32(acc[j]);
     }
     }
     fence_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)

@@ -272,14 +272,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const __grid_
         if (warp == 0) WS_TRACE(0, 100 + kc);
         if (run_needed) {
           unsigned char* As = sA + s * kABytes;
+          float acc[kRunWs];
+          depthwise_run16(v, w, acc);
 #pragma unroll
           for (int j = 0; j < kRunWs; ++j) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int kk = 0; kk < 9; ++kk) acc = fmaf(v[2 * j + kk], w[kk], acc);
             const int row = warp * kRunWs + j;
             const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u;
-            *reinterpret_cast<uint32_t*>(As + off) = to_tf32(acc);
+            *reinterpret_cast<uint32_t*>(As + off) = to_tf32(acc[j]);
           }
         }
         fence_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
