@@ -190,6 +190,15 @@ __device__ __forceinline__ void gelu_erf_fast2(u64 z2, float& o0, float& o1) {
   o1 = fmaxf(z1, 0.0f) - fabsf(t1);
 }
 
+// tanh of two columns: the scale, the 1 + e and the final fma are packed; same operations as tanh_fast (identical bits)
+__device__ __forceinline__ void tanh_fast2(u64 z2, float& o0, float& o1) {
+  float s0, s1;
+  unpack2(mul2(z2, pack2(2.88539008177792681472f, 2.88539008177792681472f)), s0, s1);
+  float d0, d1;
+  unpack2(add2(pack2(1.0f, 1.0f), pack2(ex2_approx(s0), ex2_approx(s1))), d0, d1);
+  unpack2(fma2(pack2(-2.0f, -2.0f), pack2(rcp_approx(d0), rcp_approx(d1)), pack2(1.0f, 1.0f)), o0, o1);
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_apply(float z);
 
@@ -198,6 +207,8 @@ __device__ __forceinline__ void act_apply2(float acc0, float acc1, float b0, flo
   const u64 z2 = add2(pack2(acc0, acc1), pack2(b0, b1));
   if (ACT == TASR_ACT_GELU_ERF) {
     gelu_erf_fast2(z2, o0, o1);
+  } else if (ACT == TASR_ACT_TANH) {
+    tanh_fast2(z2, o0, o1);
   } else {
     float z0, z1;
     unpack2(z2, z0, z1);

@@ -30,6 +30,17 @@ int main(int argc, char** argv) {
   int (*p_tasr_unpack_pcm16)(const int16_t*, const int64_t*, const int32_t*, int32_t, int32_t, float*, int64_t, tasr_stream_t);
   int (*p_tasr_specaugment_f32)(float*, const int32_t*, int32_t, int32_t, int32_t, const int32_t*, int32_t, const int32_t*,
                                 int32_t, tasr_stream_t);
+  int (*p_tasr_logmel_f32_single_pass)(const TasrFeaturizer*, const float*, const int32_t*, int32_t, int64_t, float*, int32_t,
+                                       int32_t*, int32_t, float*, TasrDeferredGain*, tasr_stream_t);
+  int (*p_tasr_sepconv1d_tf32_ragged_lean)(const TasrSepConvPlan*, const float*, const int32_t*, int32_t, int32_t, int32_t,
+                                           float*, int32_t, int32_t, const TasrDeferredGain*, tasr_stream_t);
+  int32_t (*p_tasr_sepconv_ragged_margin)(void);
+  int (*p_tasr_conv2d_plan_create)(const float*, const float*, const float*, const float*, int32_t, TasrConv2dPlan**, tasr_stream_t);
+  int (*p_tasr_conv2d_output_shape)(int32_t, int32_t, int32_t*, int32_t*, int32_t*, int32_t*);
+  int (*p_tasr_conv2d_subsample_ragged)(const TasrConv2dPlan*, const float*, const int32_t*, int32_t, int32_t, int32_t, void*,
+                                        float*, tasr_stream_t);
+  LOAD(tasr_logmel_f32_single_pass); LOAD(tasr_sepconv1d_tf32_ragged_lean); LOAD(tasr_sepconv_ragged_margin);
+  LOAD(tasr_conv2d_plan_create); LOAD(tasr_conv2d_output_shape); LOAD(tasr_conv2d_subsample_ragged);
   LOAD(tasr_version); LOAD(tasr_last_error); LOAD(tasr_featurizer_create); LOAD(tasr_absmax_f32); LOAD(tasr_logmel_f32);
   LOAD(tasr_sepconv1d_f32); LOAD(tasr_conv_lengths_mask); LOAD(tasr_unpack_pcm16); LOAD(tasr_specaugment_f32);
 
@@ -42,6 +53,17 @@ int main(int argc, char** argv) {
   if (p_tasr_sepconv1d_f32(0, 1, 9, 0, 0, 1, 0) != TASR_ERR_BAD_ARG) { printf("sepconv null check\n"); return 1; }
   if (p_tasr_unpack_pcm16(0, 0, 0, 1, 4, 0, 4, 0) != TASR_ERR_BAD_ARG) { printf("unpack null check\n"); return 1; }
   if (p_tasr_specaugment_f32(0, 0, 1, 1, 80, 0, 0, 0, 0, 0) != TASR_ERR_BAD_ARG) { printf("specaugment null check\n"); return 1; }
+
+  /* the round-1 additions: single-pass featurizer, lean ragged conv, Conv2dSubsampling */
+  if (p_tasr_logmel_f32_single_pass(0, 0, 0, 1, 4, 0, 1, 0, -1, 0, 0, 0) != TASR_ERR_BAD_ARG) { printf("single-pass null check\n"); return 1; }
+  if (p_tasr_sepconv1d_tf32_ragged_lean(0, 0, 0, 0, 1, 9, 0, 1, 39, 0, 0) != TASR_ERR_BAD_ARG) { printf("lean null check\n"); return 1; }
+  if (p_tasr_sepconv_ragged_margin() < 38) { printf("ragged margin\n"); return 1; }
+  { TasrConv2dPlan* cp = 0;
+    if (p_tasr_conv2d_plan_create(0, 0, 0, 0, 144, &cp, 0) != TASR_ERR_BAD_ARG || cp != 0) { printf("conv2d plan null check\n"); return 1; }
+    int32_t h1, w1, h2, w2;
+    if (p_tasr_conv2d_output_shape(1498, 80, &h1, &w1, &h2, &w2) != TASR_OK || h1 != 749 || w1 != 40 || h2 != 375 || w2 != 20) {
+      printf("conv2d output shape %d %d %d %d\n", h1, w1, h2, w2); return 1; }
+    if (p_tasr_conv2d_subsample_ragged(0, 0, 0, 1, 8, 80, 0, 0, 0) != TASR_ERR_BAD_ARG) { printf("conv2d ragged null check\n"); return 1; } }
 
   /* a frame geometry the kernels are not built for is TASR_ERR_UNSUPPORTED at handle creation */
   TasrFeatParams p;
