@@ -53,7 +53,7 @@ struct __align__(16) Smem {
   int32_t vcum[kChunkUtt + 1];             // exclusive prefix of valid 32-frame tiles per utterance of the chunk
   int32_t pcum[kChunkUtt + 1];             // exclusive prefix of 128-row padding chunks per utterance
   int32_t wsum[2][kWarps];
-  int2 list[kThreads];                     // this CTA's next valid tiles: (utterance within chunk, tile index)
+  int4 list[kThreads];                     // this CTA's next valid tiles: (utterance within chunk, tile index, len, -)
   float4 band_w[kMelBandMaxW4];            // generic path only
   MelBands bands;                          // generic path only
 };
@@ -204,23 +204,23 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
   if (tid < nlist) {
     const int x = jv - voff + tid * (int)gridDim.x;
     const int u = find(S.vcum, x);
-    S.list[tid] = make_int2(u, x - S.vcum[u]);
+    S.list[tid] = make_int4(u, x - S.vcum[u], a.len[cb + u], 0);   // the length rides along: no global load in the tile loop
   }
   __syncthreads();
 #pragma unroll 1
   for (int li = 0; li < nlist; ++li) {
-    const int2 item = S.list[li];
+    const int4 item = S.list[li];
     const int b = cb + item.x;
     const int tf = item.y;
 
     if (li + 1 < nlist && tid < 168) {  // next tile -> L2: 5360 samples = 167.5 lines of 128 B
-      const int2 nxt = S.list[li + 1];
+      const int4 nxt = S.list[li + 1];
       const float* nrow = a.wav + (size_t)(cb + nxt.x) * a.row_stride;
       const int ns = nxt.y * kTileFrames * kFrameStep + tid * 32;
-      if (ns < a.len[cb + nxt.x]) prefetch_l2(nrow + ns);
+      if (ns < nxt.z) prefetch_l2(nrow + ns);
     }
 
-    const int n = a.len[b];
+    const int n = item.z;
     const int Tb = frames_of(n, a);
     const int f0 = tf * kTileFrames;
     const int rows = min(kTileFrames, a.T_max - f0);
