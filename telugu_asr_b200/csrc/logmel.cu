@@ -406,7 +406,8 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
       }
       st_global_v4(orow + 4 * i, o);
     }
-    __syncthreads();  // stage (= scratch) and wav are reused by the next tile
+    // No barrier here: the next tile first writes only `wav` (last read before the post-FFT barrier above), and its
+    // staging barrier orders these reads of `stage` before the next FFT phase overwrites the scratch.
   }
   jv += nlist * (int)gridDim.x;   // (the tile loop ends on a barrier, so the list can be rewritten)
   }
