@@ -304,10 +304,11 @@ extern "C" int tasr_sepconv_plan_create(const TasrSepConvLayer* L, TasrSepConvPl
   p->d_pad_in = nullptr;
   p->d_pad_out = nullptr;
   p->pad_ready = 0;
-  {  // the persistent warp-specialised kernel of sepconv_ws.cu (identical bits) is the default where it is faster:
-     // the wide layers (c_in >= 192: 82 vs 90 and 63 vs 69 us on config 3).  TASR_SEPCONV_WS=0 / 1: never / always.
+  {  // the persistent warp-specialised kernel of sepconv_ws.cu (identical bits) is the default: 49 / 70 / 57 us against
+     // 56 / 90 / 69 us for the per-tile kernel on config 3; launches outside its limits (batch > 512, ...) fall back
+     // to the per-tile kernel by themselves.  TASR_SEPCONV_WS=0 / 1: never / always try it.
     const char* e = getenv("TASR_SEPCONV_WS");
-    p->use_ws = e ? (e[0] == '1' ? 1 : 0) : (L->c_in >= 192 ? 1 : 0);
+    p->use_ws = e ? (e[0] == '1' ? 1 : 0) : 1;
   }
   int rc = check_cuda(cudaGetDevice(&p->device), "cudaGetDevice");
   if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_pad_in, (size_t)9 * L->c_in * sizeof(float)), "cudaMalloc pad rows");
@@ -357,7 +358,7 @@ static int launch_tf32(const char* who, const TasrSepConvPlan* p, const float* x
   a.in_peak = gain ? gain->peak : nullptr;
   a.in_scale2 = gain ? gain->log_scale_x2 : 0.0f;
   a.in_floor = gain ? gain->log_floor : 0.0f;
-  if (p->use_ws && !gain) {
+  if (p->use_ws) {
     const int wrc = tasr_sepconv_ws_launch(p, a, B, (cudaStream_t)stream);
     if (wrc >= 0) return wrc;            // launched (TASR_OK) or failed with an error code
   }

@@ -1,6 +1,6 @@
-// SeparableConv1D forward, persistent warp-specialised TF32 kernel (sm_100a).  Default for layers with
-// c_in >= 192 (layers 2 and 3 of the reference stack); TASR_SEPCONV_WS=0 at plan creation selects the per-tile
-// kernel of sepconv_tf32.cu everywhere, =1 this kernel everywhere.
+// SeparableConv1D forward, persistent warp-specialised TF32 kernel (sm_100a).  The default for every layer whose
+// shape is inside its limits (the launcher falls back to the per-tile kernel of sepconv_tf32.cu otherwise);
+// TASR_SEPCONV_WS=0 at plan creation selects the per-tile kernel everywhere.
 //
 // Same arithmetic, operand layouts and summation order as sepconv_tf32.cu (its output is bit-identical,
 // tested); what changes is the schedule.  sepconv_tf32_kernel runs one CTA per 128-frame tile and walks
@@ -66,7 +66,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 struct WsLayout {
-  uint32_t a, b, xs, stg, bias, cum_c, cum_f, list_c, list_cf, list_f, bars, tmem_slot, total;
+  uint32_t a, b, xs, stg, bias, cum_c, cum_f, list_c, list_cf, list_f, list_gc, bars, tmem_slot, total;
 };
 __host__ __device__ inline WsLayout ws_layout(int NT, int C_out) {
   WsLayout L;
@@ -81,6 +81,7 @@ __host__ __device__ inline WsLayout ws_layout(int NT, int C_out) {
   L.list_c = o; o += kListCap * 4;
   L.list_cf = o; o += kListCap * 4;
   L.list_f = o; o += kListCap * 4;
+  L.list_gc = o; o += kListCap * 4;
   o = (o + 7u) & ~7u;
   L.bars = o; o += 32 * 8;
   L.tmem_slot = o; o += 16;
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const __grid_
   int32_t* list_c = reinterpret_cast<int32_t*>(sm + L.list_c);
   int32_t* list_cf = reinterpret_cast<int32_t*>(sm + L.list_cf);   // cf of each compute item (rows 2t >= cf are padding)
   int32_t* list_f = reinterpret_cast<int32_t*>(sm + L.list_f);
+  float* list_gc = reinterpret_cast<float*>(sm + L.list_gc);     // deferred input gain of each compute item (2 log g), see SepArgs::in_peak
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem_slot);
   const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sm + L.b), bar_u = smem_u32(sm + L.bars);
   // barriers: A full (one arrival per depthwise warp) / A empty (commit), B full (tx) / B empty (commit),
@@ -220,6 +222,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const __grid_
     const int tile = r / wa.n_split, nh = r - tile * wa.n_split;
     list_c[k] = (u << 16) | (tile << 4) | nh;
     list_cf[k] = (a.len0 != nullptr) ? ((max(a.len0[u], 0) + (1 << a.shift) - 1) >> a.shift) : 0x7fffffff;
+    float gc = 0.0f;
+    if (a.in_peak != nullptr) {            // g = 1/(peak+1e-9) as the reference rounds it (src/speech_featurizer.py:70)
+      float lg;
+      const float g = __fdiv_rn(1.0f, __fadd_rn(a.in_peak[u], 1e-9f));
+      asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(g));
+      gc = a.in_scale2 * lg;
+    }
+    list_gc[k] = gc;
   }
   for (int k = tid; k < n_f; k += kWsThreads) {
     const int j = me + k * G;
@@ -265,6 +275,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const __grid_
           const float* xw = xs_f + (size_t)sx * (kXBytes / 4) + (size_t)(2 * warp * kRunWs) * kKC + lane;
 #pragma unroll
           for (int i = 0; i < kWinWs; ++i) v[i] = xw[i * kKC];
+          if (a.in_peak != nullptr) {      // rows of the data get the deferred gain and the floor; padding rows stay 0.0
+            const float gc = list_gc[k];
+            const int cf = list_cf[k];
+            if (r0 + kWinWs <= cf) {
+#pragma unroll
+              for (int i = 0; i < kWinWs; ++i) v[i] = fmaxf(v[i] + gc, a.in_floor);
+            } else {
+#pragma unroll
+              for (int i = 0; i < kWinWs; ++i) v[i] = (r0 + i < cf) ? fmaxf(v[i] + gc, a.in_floor) : v[i];
+            }
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_xempty(sx));            // this warp has its window in registers

@@ -526,8 +526,8 @@ def test_featurizer_waveform_mode(cuda_device):
 
 
 def test_sepconv_persistent_kernel_matches_per_tile_kernel_bitwise(cuda_device, monkeypatch):
-    """csrc/sepconv_ws.cu (persistent, warp-specialised; default for c_in >= 192, TASR_SEPCONV_WS=1/0 forces it
-    on/off for every layer) and csrc/sepconv_tf32.cu (one CTA per tile) do the same arithmetic in the same order:
+    """csrc/sepconv_ws.cu (persistent, warp-specialised; the default, TASR_SEPCONV_WS=1/0 forces it on/off for every
+    layer) and csrc/sepconv_tf32.cu (one CTA per tile) do the same arithmetic in the same order:
     identical bits — dense, ragged, and ragged with lean intermediates on NaN-poisoned buffers."""
     from telugu_asr_b200.synth import draw_lengths
     lens = draw_lengths(40, 1600, 240000, seed=13)
@@ -971,3 +971,29 @@ def test_conv2d_subsampling_ragged_is_bit_identical_to_dense(cuda_device, T):
     assert torch.equal(res[True][1], res[False][1])
     assert not torch.isnan(res[True][0]).any()
     assert torch.equal(res[True][0], res[False][0])
+
+
+def test_persistent_kernel_applies_the_deferred_gain_bitwise(cuda_device, monkeypatch):
+    """Single-pass front end with the first layer on the persistent kernel (TASR_SEPCONV_WS=1) vs on the per-tile
+    kernel (=0): the deferred gain and floor are applied to the same rows with the same arithmetic — identical bits."""
+    from telugu_asr_b200.synth import draw_lengths
+    lens = draw_lengths(24, 1600, 240000, seed=14)
+    lens[0], lens[1], lens[2] = 240000, 399, 400
+    wav, ln = oracle.make_waveforms(lens, seed=14, dist="tilt")
+    wav[4, : ln[4] // 3] = 0.0
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    w, l = gpu(wav, cuda_device), gpu(ln, cuda_device)
+    res = {}
+    for ws in ("1", "0"):
+        monkeypatch.setenv("TASR_SEPCONV_WS", ws)
+        fe = tasr.FrontEnd(math="tf32", single_pass=True)
+        fe.set_weights(weights, cuda_device)
+        _native.poison_allocations = True
+        try:
+            res[ws] = _call_or_skip(fe, w, l)
+            torch.cuda.synchronize()
+        finally:
+            _native.poison_allocations = False
+    for a, b in zip(res["1"], res["0"]):
+        assert torch.equal(a, b)
+    assert not torch.isnan(res["1"][0]).any()
