@@ -506,6 +506,10 @@ def main():
                        "pointwise_math": math_mode + (" (tcgen05 kind::tf32, fp32 accumulate)" if math_mode == "tf32" else " (CUDA-core FMA)"),
                        "l2": "inputs larger than L2: 246 MB padded waveforms (128 MB of samples read) per step and two steps in flight vs 126 MB L2; no flush needed",
                        "parallelism": f"dp{world} by utterance, no data-path collective",
+                       "featurizer": ("single pass: the log-mel kernel finds max|x| while it stages the samples and the first separable conv "
+                                      "applies 2 log(gain) and the floor (float32-rounding differences only, tests/test_gpu_parity.py); "
+                                      "no separate peak pass") if getattr(fe, "single_pass", False) and math_mode == "tf32"
+                                     else "two passes: tasr_absmax_f32, then the log-mel kernel",
                        "intermediates": ("lean: the log-mel tensor and the activations of layers 1-2 are not written far inside the "
                                          "collate padding (no kernel reads them there); encoder input, mask and lengths are bit-identical "
                                          "to the fully materialised run (tests/test_gpu_parity.py)") if lean else "fully materialised",
