@@ -182,3 +182,31 @@ def test_builtin_reference_config_equals_the_reference_yaml():
     assert isinstance(sc["output_floor"], float) and sc["output_floor"] == 1e-9   # `1e-9` in the YAML: OmegaConf reads a float
     sc2, _, _ = tasr.load_reference_yaml("/root/reference/config/conformer.yaml")
     assert sc2 == sc
+
+
+def test_conv2d_subsampling_host_mirror_without_gpu():
+    """Conv2dSubsampling (src/models/conformer/encoder.py:9-48): constructor defaults, the geometry it refuses, the
+    static output shape against the oracle's TensorFlow "SAME" arithmetic — host logic only, no device needed."""
+    import oracle
+    layer = tasr.Conv2dSubsampling({"name": "conv2d", "filters": 144, "kernel_size": 3, "strides": 2, "padding": "same"})
+    assert (layer.filter, layer.kernel_size, layer.stride, layer.padding) == (144, 3, 2, "same")
+    assert tasr.Conv2dSubsampling({}).filter == 128                       # encoder.py:22 default
+    for bad in ({"kernel_size": 5}, {"strides": 1}, {"padding": "valid"}):
+        with pytest.raises(NotImplementedError):
+            tasr.Conv2dSubsampling({"filters": 144, **bad})
+    for T in (1, 2, 37, 38, 1497, 1498):
+        h1, _, _ = oracle.same_pads(T, 3, 2)
+        h2, _, _ = oracle.same_pads(h1, 3, 2)
+        assert layer.output_shape(T, 80) == (h1, 40, h2, 20)
+        assert layer.compute_output_shape((7, T, 80, 1)) == (7, h2, 20 * 144)
+    with pytest.raises(RuntimeError):                                     # no CPU path
+        layer([torch.zeros(1, 8, 80, 1), None])
+
+
+def test_front_end_defaults_and_flags():
+    fe = tasr.FrontEnd()
+    assert fe.single_pass and fe.lean_intermediates and fe.subsampling.math == "tf32"
+    assert fe.featurizer.supports_single_pass()
+    assert not tasr.SpeechFeaturizer(**{**tasr.REFERENCE_SPEECH_CONFIG, "normalize_signal": False}).supports_single_pass()
+    assert not tasr.SpeechFeaturizer(**{**tasr.REFERENCE_SPEECH_CONFIG, "pad_end": True}).supports_single_pass()
+    assert tasr.Conv1DSubsamplingLayer.ragged_margin() >= 38               # rows a lean producer must keep filled
