@@ -482,9 +482,28 @@ extern "C" void tasr_debug_ws_trace(long long* dev_buf) { g_ws_trace = dev_buf; 
 
 // Returns TASR_OK after launching, or a negative value when this shape is not handled by the persistent
 // kernel (the caller then uses sepconv_tf32_kernel).
-int tasr_sepconv_ws_launch(const TasrSepConvPlan* p, const SepArgs& sa, int32_t B, cudaStream_t st) {
+int tasr_sepconv_ws_launch(const TasrSepConvPlan* p, const SepArgs& sa_all, int32_t B_all, cudaStream_t st) {
+  if (B_all > kMaxUtt) {
+    // The kernel indexes at most kMaxUtt utterances in shared memory: a larger batch runs as consecutive sub-batches
+    // (utterances are independent; each sub-launch is a full persistent grid) — when a sub-batch is worth a persistent
+    // launch (measured: 30 s x 1024 8.4 -> 9.1 M audio-s/s, but 1 s x 1024 3.1 -> 2.8 M: short tensors stay per-tile).
+    const long long items = (long long)kMaxUtt * ((sa_all.T_out + kMT - 1) / kMT) * p->n_split;
+    if (items < 8LL * sm_count()) return -1;
+    for (int32_t b0 = 0; b0 < B_all; b0 += kMaxUtt) {
+      SepArgs sub = sa_all;
+      sub.x = sa_all.x + (size_t)b0 * sa_all.T_in * p->L.c_in;
+      sub.y = sa_all.y + (size_t)b0 * sa_all.T_out * p->L.c_out;
+      if (sa_all.len0) sub.len0 = sa_all.len0 + b0;
+      if (sa_all.in_peak) sub.in_peak = sa_all.in_peak + b0;
+      const int rc = tasr_sepconv_ws_launch(p, sub, B_all - b0 < kMaxUtt ? B_all - b0 : kMaxUtt, st);
+      if (rc != TASR_OK) return (b0 == 0) ? rc : (rc < 0 ? fail(TASR_ERR_CUDA, "sepconv_ws: sub-batch launch refused after earlier sub-batches ran") : rc);
+    }
+    return TASR_OK;
+  }
+  const SepArgs& sa = sa_all;
+  const int32_t B = B_all;
   const int n_tiles = (sa.T_out + kMT - 1) / kMT;
-  if (B > kMaxUtt || n_tiles > 0xfff || p->n_split > 15 || 2 * p->NT > kTmemColsWs) return -1;
+  if (n_tiles > 0xfff || p->n_split > 15 || 2 * p->NT > kTmemColsWs) return -1;
   const int grid = sm_count();
   const long long dense = (long long)B * n_tiles * p->n_split;
   if ((dense + grid - 1) / grid > kListCap) return -1;

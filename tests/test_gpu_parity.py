@@ -997,3 +997,23 @@ def test_persistent_kernel_applies_the_deferred_gain_bitwise(cuda_device, monkey
     for a, b in zip(res["1"], res["0"]):
         assert torch.equal(a, b)
     assert not torch.isnan(res["1"][0]).any()
+
+
+def test_persistent_kernel_sub_batches_above_512_utterances(cuda_device, monkeypatch):
+    """More than 512 utterances run through the persistent kernel as consecutive sub-batches: identical bits to the
+    per-tile kernel, single-pass front end (deferred gain pointers are offset per sub-batch too)."""
+    from telugu_asr_b200.synth import draw_lengths
+    lens = draw_lengths(700, 400, 160000, seed=15)      # long enough that the sub-batches are worth persistent launches
+    lens[0], lens[511], lens[512], lens[699] = 160000, 399, 160000, 16000
+    wav, ln = oracle.make_waveforms(lens, seed=15, dist="tilt")
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    w, l = gpu(wav, cuda_device), gpu(ln, cuda_device)
+    res = {}
+    for ws in ("1", "0"):
+        monkeypatch.setenv("TASR_SEPCONV_WS", ws)
+        fe = tasr.FrontEnd(math="tf32")
+        fe.set_weights(weights, cuda_device)
+        res[ws] = _call_or_skip(fe, w, l)
+        torch.cuda.synchronize()
+    for a, b in zip(res["1"], res["0"]):
+        assert torch.equal(a, b)
