@@ -250,7 +250,10 @@ int tasr_conv2d_subsample(const TasrConv2dPlan* plan, const float* feat, int32_t
  * tasr_conv2d_subsample on the same (zero-padded) input. */
 int tasr_conv2d_plan_prepare_ragged(TasrConv2dPlan* plan, int32_t w, tasr_stream_t stream);
 int tasr_conv2d_subsample_ragged(const TasrConv2dPlan* plan, const float* feat, const int32_t* n_frames, int32_t batch,
-                                 int32_t t, int32_t w, void* h1_workspace, float* out, tasr_stream_t stream);
+                                 int32_t t, int32_t w, void* h1_workspace, float* out,
+                                 const TasrDeferredGain* input_gain_or_null, tasr_stream_t stream);
+/* input_gain_or_null (host struct): feat comes from tasr_logmel_f32_single_pass and every row t < n_frames[b] is read as
+ * max(feat + 2*log(1/(peak[b]+1e-9)), log_floor) by the first convolution. */
 
 /* SpecAugment, deterministic half (replaces FreqMasking.augment / TimeMasking.augment,
  * src/augmentations/specaugment.py:6-62, applied per utterance at src/dataset.py:172): in place on

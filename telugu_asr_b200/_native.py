@@ -75,7 +75,7 @@ _SIGNATURES = {
     "tasr_conv2d_output_shape": (C.c_int, [_i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "tasr_conv2d_subsample": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "tasr_conv2d_plan_prepare_ragged": (C.c_int, [_vp, _i32, _vp]),
-    "tasr_conv2d_subsample_ragged": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "tasr_conv2d_subsample_ragged": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, C.POINTER(TasrDeferredGain), _vp]),
     "tasr_specaugment_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp]),
     "tasr_audio_mask": (C.c_int, [_vp, _i64, _i32, C.c_float, _vp, _vp]),
     "tasr_count_nonzero_frames": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),

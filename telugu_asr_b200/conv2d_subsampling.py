@@ -104,7 +104,10 @@ class Conv2dSubsampling:
         _, _, h2, w2 = self.output_shape(input_shape[1], input_shape[2])
         return (input_shape[0], h2, w2 * self.filter)
 
-    def __call__(self, inputs, training: bool = False, **kwargs):
+    def __call__(self, inputs, training: bool = False, input_gain=None, **kwargs):
+        """`input_gain` (a speech_featurizer.DeferredGain): the features are the raw output of
+        `featurize_batch(single_pass=True)`; the first convolution adds the gain and the floor as it reads them
+        (needs lengths and assume_zero_padding)."""
         outputs, outputs_length = inputs                                   # encoder.py:56
         x = _native.require_cuda(outputs, "outputs")
         if x.dim() != 4 or x.shape[-1] != 1:
@@ -133,7 +136,10 @@ class Conv2dSubsampling:
                     _native.check(L.tasr_conv2d_plan_prepare_ragged(self._plan, W, st))
                     self._ragged_w = W
                 _native.check(L.tasr_conv2d_subsample_ragged(self._plan, x.data_ptr(), ln.data_ptr(), B, T, W,
-                                                             work.data_ptr(), out.data_ptr(), st))
+                                                             work.data_ptr(), out.data_ptr(),
+                                                             C.byref(input_gain.struct) if input_gain is not None else None, st))
+            elif input_gain is not None:
+                raise ValueError("input_gain needs outputs_length and assume_zero_padding=True (the ragged path)")
             else:
                 _native.check(L.tasr_conv2d_subsample(self._plan, x.data_ptr(), B, T, W, work.data_ptr(), out.data_ptr(), st))
             out_len = None

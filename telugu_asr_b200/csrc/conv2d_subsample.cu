@@ -67,7 +67,8 @@ template <int MAXT, int MINB>   // (288, 3) for filters <= 144: 72 registers, th
 __global__ void __launch_bounds__(MAXT, MINB) conv2d_first_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                             const float* __restrict__ b1, __half* __restrict__ h1,
                                                             int T, int W, int H1, int W1, int F, int pt, int pl,
-                                                            const int32_t* __restrict__ n_frames, int pt2, int H2, int rows_per_tile) {
+                                                            const int32_t* __restrict__ n_frames, int pt2, int H2, int rows_per_tile,
+                                                            const float* __restrict__ in_peak, float in_scale2, float in_floor) {
   extern __shared__ float xs[];                      // [2*kC1Rows+1][SW], SW = 2*W1+1 columns starting at column -pl
   const int SW = 2 * W1 + 1;
   const int b = blockIdx.y, i0 = blockIdx.x * kC1Rows;
@@ -84,11 +85,26 @@ __global__ void __launch_bounds__(MAXT, MINB) conv2d_first_kernel(const float* _
     const int tail_begin = 2 * (H2 - 1 - rows_per_tile) - pt2;
     if (i0 >= head_end && i0 + nrows <= tail_begin) return;
   }
+  // deferred gain of the single-pass featurizer (tasr_logmel_f32_single_pass): a data row is read as
+  // max(x + 2 log(1/(peak+1e-9)), log floor); padding stays 0.0
+  float gc = 0.0f;
+  const bool fix = (in_peak != nullptr);
+  if (fix) {
+    float lg;
+    const float g = __fdiv_rn(1.0f, __fadd_rn(in_peak[b], 1e-9f));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(g));
+    gc = in_scale2 * lg;
+  }
   const float* xb = x + (size_t)b * T * W;
   for (int k = threadIdx.x; k < (2 * kC1Rows + 1) * SW; k += blockDim.x) {
     const int d = k / SW, cc = k - d * SW;
     const int r = 2 * i0 + d - pt, c = cc - pl;
-    xs[k] = (r >= 0 && r < n_valid && c >= 0 && c < W) ? __ldg(xb + (size_t)r * W + c) : 0.0f;
+    float v = 0.0f;
+    if (r >= 0 && r < n_valid && c >= 0 && c < W) {
+      v = __ldg(xb + (size_t)r * W + c);
+      if (fix) v = fmaxf(v + gc, in_floor);
+    }
+    xs[k] = v;
   }
   const int f4n = F >> 2;
   const int f = (threadIdx.x % f4n) * 4, p0 = threadIdx.x / f4n;
@@ -393,7 +409,7 @@ extern "C" int tasr_conv2d_output_shape(int32_t t, int32_t w, int32_t* h1, int32
 }
 
 static int conv2d_launch(const char* who, const TasrConv2dPlan* p, const float* feat, const int32_t* n_frames, int32_t B,
-                         int32_t T, int32_t W, void* h1, float* out, tasr_stream_t stream) {
+                         int32_t T, int32_t W, void* h1, float* out, tasr_stream_t stream, const TasrDeferredGain* gain = nullptr) {
   if (!p || !feat || !h1 || !out) return fail(TASR_ERR_BAD_ARG, "%s: null argument", who);
   if (B < 0 || T < 0 || W < 0) return fail(TASR_ERR_BAD_ARG, "%s: negative size", who);
   if (!aligned16(h1) || !aligned16(out)) return fail(TASR_ERR_MISALIGNED, "%s: h1/out must be 16-byte aligned", who);
@@ -416,10 +432,12 @@ static int conv2d_launch(const char* who, const TasrConv2dPlan* p, const float* 
     if (smem1 > 48 * 1024) return fail(TASR_ERR_UNSUPPORTED, "%s: feature width %d too large", who, W);
     if (8 * (F / 4) <= 288)
       conv2d_first_kernel<288, 3><<<grid1, 8 * (F / 4), smem1, st>>>(feat, p->d_w1, p->d_b1, reinterpret_cast<__half*>(h1), T, W, H1, W1,
-                                                                     F, pt1, pl1, n_frames, pt2, H2, rows_per_tile);
+                                                                     F, pt1, pl1, n_frames, pt2, H2, rows_per_tile,
+                                                                     gain ? gain->peak : nullptr, gain ? gain->log_scale_x2 : 0.0f, gain ? gain->log_floor : 0.0f);
     else
       conv2d_first_kernel<512, 1><<<grid1, 8 * (F / 4), smem1, st>>>(feat, p->d_w1, p->d_b1, reinterpret_cast<__half*>(h1), T, W, H1, W1,
-                                                                     F, pt1, pl1, n_frames, pt2, H2, rows_per_tile);
+                                                                     F, pt1, pl1, n_frames, pt2, H2, rows_per_tile,
+                                                                     gain ? gain->peak : nullptr, gain ? gain->log_scale_x2 : 0.0f, gain ? gain->log_floor : 0.0f);
     TASR_LAUNCH_CHECK("conv2d_first_kernel");
   }
   C2Args a;
@@ -468,7 +486,9 @@ extern "C" int tasr_conv2d_plan_prepare_ragged(TasrConv2dPlan* p, int32_t W, tas
 }
 
 extern "C" int tasr_conv2d_subsample_ragged(const TasrConv2dPlan* p, const float* feat, const int32_t* n_frames, int32_t B,
-                                            int32_t T, int32_t W, void* h1, float* out, tasr_stream_t stream) {
+                                            int32_t T, int32_t W, void* h1, float* out, const TasrDeferredGain* gain,
+                                            tasr_stream_t stream) {
   if (!n_frames) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample_ragged: null n_frames");
-  return conv2d_launch("tasr_conv2d_subsample_ragged", p, feat, n_frames, B, T, W, h1, out, stream);
+  if (gain && !gain->peak) return fail(TASR_ERR_BAD_ARG, "tasr_conv2d_subsample_ragged: deferred gain without a peak pointer");
+  return conv2d_launch("tasr_conv2d_subsample_ragged", p, feat, n_frames, B, T, W, h1, out, stream, gain);
 }

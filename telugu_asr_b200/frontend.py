@@ -12,7 +12,7 @@ import yaml
 from .speech_featurizer import SpeechFeaturizer
 from .subsampling import Conv1DSubsamplingLayer
 
-__all__ = ["FrontEnd", "CapturedFrontEnd", "InterleavedFrontEnd", "REFERENCE_SPEECH_CONFIG", "REFERENCE_SUBSAMPLING_CONFIG", "load_reference_yaml"]
+__all__ = ["FrontEnd", "ConformerFrontEnd", "CapturedFrontEnd", "InterleavedFrontEnd", "REFERENCE_SPEECH_CONFIG", "REFERENCE_SUBSAMPLING_CONFIG", "load_reference_yaml"]
 
 # config/model.yaml:1-17
 REFERENCE_SPEECH_CONFIG = dict(
@@ -94,6 +94,40 @@ class FrontEnd:
         if return_features:
             return out, mask, len3, feats, n_frames
         return out, mask, len3
+
+
+class ConformerFrontEnd:
+    """The conformer configuration's front end (config/conformer.yaml): waveforms -> log-mel -> Conv2dSubsampling
+    (src/models/conformer/encoder.py:9-67) -> ([B, ceil(T/4), 20*filters], lengths ceil(n_frames/2) as the reference
+    computes them).  Same device-side economy as FrontEnd: one pass over the waveform (the first convolution applies
+    the deferred gain and floor), the feature tensor written only where it is read, the collate padding of the conv
+    outputs filled with its constant pattern instead of being computed."""
+
+    def __init__(self, speech_config: dict | None = None, subsampling_config: dict | None = None, device=None, seed: int = 0,
+                 single_pass: bool = True):
+        from .conv2d_subsampling import Conv2dSubsampling
+        self.featurizer = SpeechFeaturizer(**(speech_config or REFERENCE_SPEECH_CONFIG))
+        self.subsampling = Conv2dSubsampling(subsampling_config or dict(name="conv2d", filters=144, kernel_size=3, strides=2,
+                                                                        padding="same"), seed=seed)
+        self.device = torch.device(device) if device is not None else None
+        self.single_pass = bool(single_pass)
+
+    def set_weights(self, weights, device=None):
+        self.subsampling.set_weights(weights, device or self.device)
+
+    def __call__(self, wav: torch.Tensor, lengths: torch.Tensor | None = None, max_length: int | None = None):
+        t_max = None
+        if max_length is not None:
+            t_max = max(0, int(self.featurizer.get_nframes(int(max_length))))
+        sub = self.subsampling
+        if (self.single_pass and sub.assume_zero_padding and self.featurizer.supports_single_pass()
+                and self.featurizer.feature_type == "log_mel_spectrogram"):
+            feats, n_frames, gain = self.featurizer.featurize_batch(wav, lengths, t_max=t_max, pad_fill_rows=0, single_pass=True)
+            out, out_len = sub([feats, n_frames], input_gain=gain)
+        else:
+            feats, n_frames = self.featurizer.featurize_batch(wav, lengths, t_max=t_max)
+            out, out_len = sub([feats, n_frames])
+        return out, out_len
 
 
 class CapturedFrontEnd:

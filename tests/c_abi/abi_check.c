@@ -38,7 +38,7 @@ int main(int argc, char** argv) {
   int (*p_tasr_conv2d_plan_create)(const float*, const float*, const float*, const float*, int32_t, TasrConv2dPlan**, tasr_stream_t);
   int (*p_tasr_conv2d_output_shape)(int32_t, int32_t, int32_t*, int32_t*, int32_t*, int32_t*);
   int (*p_tasr_conv2d_subsample_ragged)(const TasrConv2dPlan*, const float*, const int32_t*, int32_t, int32_t, int32_t, void*,
-                                        float*, tasr_stream_t);
+                                        float*, const TasrDeferredGain*, tasr_stream_t);
   LOAD(tasr_logmel_f32_single_pass); LOAD(tasr_sepconv1d_tf32_ragged_lean); LOAD(tasr_sepconv_ragged_margin);
   LOAD(tasr_conv2d_plan_create); LOAD(tasr_conv2d_output_shape); LOAD(tasr_conv2d_subsample_ragged);
   LOAD(tasr_version); LOAD(tasr_last_error); LOAD(tasr_featurizer_create); LOAD(tasr_absmax_f32); LOAD(tasr_logmel_f32);
@@ -63,7 +63,7 @@ int main(int argc, char** argv) {
     int32_t h1, w1, h2, w2;
     if (p_tasr_conv2d_output_shape(1498, 80, &h1, &w1, &h2, &w2) != TASR_OK || h1 != 749 || w1 != 40 || h2 != 375 || w2 != 20) {
       printf("conv2d output shape %d %d %d %d\n", h1, w1, h2, w2); return 1; }
-    if (p_tasr_conv2d_subsample_ragged(0, 0, 0, 1, 8, 80, 0, 0, 0) != TASR_ERR_BAD_ARG) { printf("conv2d ragged null check\n"); return 1; } }
+    if (p_tasr_conv2d_subsample_ragged(0, 0, 0, 1, 8, 80, 0, 0, 0, 0) != TASR_ERR_BAD_ARG) { printf("conv2d ragged null check\n"); return 1; } }
 
   /* a frame geometry the kernels are not built for is TASR_ERR_UNSUPPORTED at handle creation */
   TasrFeatParams p;

@@ -1017,3 +1017,36 @@ def test_persistent_kernel_sub_batches_above_512_utterances(cuda_device, monkeyp
         torch.cuda.synchronize()
     for a, b in zip(res["1"], res["0"]):
         assert torch.equal(a, b)
+
+
+def test_conformer_front_end_single_pass_matches_two_pass_and_oracle(cuda_device):
+    """ConformerFrontEnd: waveforms -> log-mel -> Conv2dSubsampling.  Single pass over the waveform (deferred gain applied
+    by the first convolution, lean features: nothing is written past the frames) vs the two-pass run: same lengths,
+    outputs within float32-rounding distance, and inside the 1e-3 budget against the oracle chain — with every operator
+    allocation NaN-poisoned."""
+    from telugu_asr_b200.synth import draw_lengths
+    lens = draw_lengths(12, 1600, 80000, seed=17)
+    lens[0], lens[1], lens[2] = 80000, 399, 400
+    wav, ln = oracle.make_waveforms(lens, seed=17, dist="tilt")
+    wav[3, : ln[3] // 2] = 0.0
+    ws = oracle.glorot_conv2d_weights(144, seed=11)
+    w, l = gpu(wav, cuda_device), gpu(ln, cuda_device)
+    res = {}
+    for sp in (False, True):
+        fe = tasr.ConformerFrontEnd(single_pass=sp)
+        fe.set_weights(ws, cuda_device)
+        _native.poison_allocations = True
+        try:
+            res[sp] = _call_or_skip(fe, w, l)
+            torch.cuda.synchronize()
+        finally:
+            _native.poison_allocations = False
+    assert torch.equal(res[True][1], res[False][1])
+    a, b = res[True][0], res[False][0]
+    assert not torch.isnan(a).any() and a.shape == b.shape
+    scale = b.abs().max().item()
+    assert (a - b).abs().max().item() <= 2e-4 * scale
+    ref_feat, ref_nf = oracle.logmel_batch_ref(wav, ln, dtype=np.float32)
+    ref_out, ref_len = oracle.conv2d_subsample_ref(ref_feat, ref_nf, ws, dtype=np.float64)
+    assert np.abs(a.cpu().numpy() - ref_out).max() / np.abs(ref_out).max() <= SUB_TOL_TF32
+    np.testing.assert_array_equal(res[True][1].cpu().numpy(), ref_len)

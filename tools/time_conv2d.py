@@ -49,3 +49,20 @@ for mode, layer_r in (("dense", tasr.Conv2dSubsampling({"filters": 144}, seed=1,
     real_audio = float(lens_np.sum()) / 16000
     print(f"configs[2] lengths ({real_audio:.0f} real audio-s, {100 * (1 - nf.sum() / (B * T)):.0f} % padding), {mode}: "
           f"med {ts[len(ts)//2]:.3f} ms -> {real_audio / ts[len(ts)//2] * 1e3 / 1e6:.2f} M audio-s/s")
+
+# the whole conformer front end on the bench batch: waveforms -> log-mel (single pass, lean) -> Conv2dSubsampling (ragged)
+wav_np, lens_np = bench.make_batch(0, B)
+wav_d, len_d = torch.from_numpy(wav_np).to(dev), torch.from_numpy(lens_np).to(dev)
+cfe = tasr.ConformerFrontEnd(seed=1)
+cfe.subsampling.build(dev)
+for _ in range(3):
+    cfe(wav_d, len_d, max_length=int(lens_np.max()))
+torch.cuda.synchronize()
+ts = []
+for _ in range(10):
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); cfe(wav_d, len_d, max_length=int(lens_np.max())); b_.record(); torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b_))
+ts.sort()
+print(f"ConformerFrontEnd (waveform -> [B, T/4, 2880]) on configs[2]'s batch: med {ts[len(ts)//2]:.3f} ms -> "
+      f"{float(lens_np.sum()) / 16000 / ts[len(ts)//2] * 1e3 / 1e6:.2f} M audio-s/s (eager launches, one stream)")
