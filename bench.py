@@ -38,6 +38,14 @@ WORKLOAD = "configs[2]: log-mel + 3x sepconv1d subsampling to d=192, batch 256 x
 BATCH = 256
 N_LO, N_HI = 16000, 240000
 FALLBACK_HBM_GBS = 6650.0
+DISTRIBUTION = "AR(1) rho=0.97 'tilt', peak 0.5, k/32768, seeds 2+rank"
+
+
+def common_config(batch: int) -> dict:
+    """The `config` object both arms print (identical by construction: the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": batch, "distribution": DISTRIBUTION,
+            "l2": "inputs larger than L2: 246 MB padded waveforms (128 MB of samples read) per step and two steps in "
+                  "flight vs 126 MB L2; no flush needed"}
 
 
 def parse():
@@ -51,6 +59,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("TASR_CPU_SAMPLE", "256")),
                     help="utterances of the workload the CPU baseline is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE.json configs[1]/[3]/[4] measurements")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--full-intermediates", action="store_true",
                     help="materialise the log-mel tensor and every layer's activations over the whole padded batch (A/B of the lean default)")
@@ -101,7 +110,7 @@ class ClockSampler:
         0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
     }
 
-    def __init__(self, index: int, period: float = 0.02):
+    def __init__(self, index: int, period: float = 0.004):
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
         self.max_mhz = None
@@ -165,33 +174,66 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU baseline (the reference's CPU path, restated) — rank 0 only
 # ------------------------------------------------------------------------------------------
-def cpu_baseline(wav, lens, weights, n_sample: int, budget_s: float = 10.0):
-    """The CPU path on a bounded sample: the first n_sample utterances of the workload, repeated until
-    about `budget_s` seconds of CPU work have been timed (at least 2 passes); value = audio-s / mean pass."""
+def _cpu_modes(cores: int):
+    """(name, frontend_torch kwargs, torch intra-op threads): how the host cores can be used.  `intra_op` = one
+    featurizer call at a time with multi-threaded torch kernels; `utterance_parallel` = `cores` single-threaded
+    featurizer calls at a time, the reference's own parallelism (src/dataset.py:227 num_parallel_calls=AUTOTUNE),
+    convs multi-threaded; `one_thread` = everything on one core."""
+    return [("intra_op", dict(workers=1), cores), ("utterance_parallel", dict(workers=cores, conv_threads=cores), cores),
+            ("one_thread", dict(workers=1), 1)]
+
+
+def _time_cpu(fn, budget_s: float, min_passes: int = 2, max_passes: int = 200):
+    times = []
+    t_begin = time.perf_counter()
+    while len(times) < min_passes or (time.perf_counter() - t_begin < budget_s and len(times) < max_passes):
+        t0 = time.perf_counter()
+        fn()
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def cpu_baseline(wav, lens, weights, n_sample: int, budget_s: float = 8.0):
+    """The CPU path on a bounded sample: the first n_sample utterances of the workload in each way the host cores can be
+    used (about `budget_s` seconds for the all-core modes, a quarter of the sample for the one-thread mode), plus
+    BASELINE.json configs[0] (log-mel of ONE 10 s utterance).  `value` = the best all-core mode."""
     import torch
     from oracle import torch_port
     n_sample = max(1, min(n_sample, wav.shape[0]))
-    w, l = wav[:n_sample], lens[:n_sample]
     cores = os.cpu_count() or 1
+    modes = {}
+    for name, kw, thr in _cpu_modes(cores):
+        n = n_sample if thr > 1 else max(1, n_sample // 4)
+        w, l = wav[:n], lens[:n]
+        audio_s = float(l.sum()) / SAMPLE_RATE
+        torch.set_num_threads(thr)
+        torch_port.frontend_torch(w[:4], l[:4], weights, **kw)          # warm-up (thread pools, FFT plans)
+        times = _time_cpu(lambda: torch_port.frontend_torch(w, l, weights, **kw), budget_s if thr > 1 else budget_s / 2)
+        modes[name] = {"value": audio_s / (sum(times) / len(times)), "best_pass": audio_s / min(times), "threads": thr,
+                       "utterances": int(n), "passes": len(times), "cpu_seconds": round(sum(times), 2)}
+    # configs[0]: the reference's own CPU-runnable case, log-mel of one synthetic 10 s utterance
+    from telugu_asr_b200.synth import make_waveforms
+    w10, _ = make_waveforms([160000], seed=0, dist="tilt")
+    x10 = torch.from_numpy(w10[0])
+    cfg0 = {}
+    for thr in (1, cores):
+        torch.set_num_threads(thr)
+        torch_port.logmel_torch(x10)
+        times = _time_cpu(lambda: torch_port.logmel_torch(x10), 1.0, min_passes=5, max_passes=400)
+        cfg0[f"threads_{thr}"] = {"ms": 1e3 * statistics.median(times), "audio_s_per_s": 10.0 / statistics.median(times)}
     torch.set_num_threads(cores)
-    torch_port.frontend_torch(w[:4], l[:4], weights)          # warm-up (thread pools, FFT plans)
-    times = []
-    t_begin = time.perf_counter()
-    while len(times) < 2 or (time.perf_counter() - t_begin < budget_s and len(times) < 200):
-        t0 = time.perf_counter()
-        torch_port.frontend_torch(w, l, weights)
-        times.append(time.perf_counter() - t0)
-    mean = sum(times) / len(times)
-    audio_s = float(l.sum()) / SAMPLE_RATE
-    return {"value": audio_s / mean, "unit": "audio-seconds/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"first {n_sample} utterances of the workload ({audio_s:.0f} audio-s) x {len(times)} passes = "
-                      f"{sum(times):.1f} s of CPU (best pass {audio_s / min(times):.0f} audio-s/s): per-utterance "
-                      "featurizer loop + zero-pad collate + 3 separable convs, torch CPU ops (oracle/torch_port.py); "
-                      "TensorFlow reference not installable offline"}
+    best = max(("intra_op", "utterance_parallel"), key=lambda k: modes[k]["value"])
+    return {"value": modes[best]["value"], "unit": "audio-seconds/s", "cores": cores, "kind": "port", "mode": best,
+            "modes": modes, "config0_logmel_1x10s": cfg0,
+            "sample": f"first {n_sample} utterances of the workload, repeated for ~{budget_s:.0f} s per all-core mode "
+                      f"({n_sample // 4 or 1} utterances for the one-thread mode): per-utterance featurizer calls + zero-pad "
+                      "collate + 3 separable convs, torch CPU ops (oracle/torch_port.py); TensorFlow reference not "
+                      "installable offline"}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (restated; see module doc)."""
+    """--impl reference: the reference's CPU implementation of the path (restated; see module doc), with all the host
+    threads it can use - the faster of the two all-core modes of _cpu_modes, chosen in the warm-up."""
     if rank != 0:
         return
     wav, lens = make_batch(0, args.batch)
@@ -199,13 +241,19 @@ def run_reference(args, rank, world):
     import torch
     from oracle import torch_port
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     n_sample = max(1, min(args.cpu_sample, args.batch))
     warm = max(1, args.warmup)
-    torch_port.frontend_torch(wav[:4], lens[:4], weights)                       # thread pools, FFT plans
-    t0 = time.perf_counter()
-    torch_port.frontend_torch(wav[:n_sample], lens[:n_sample], weights)
-    first = time.perf_counter() - t0
+    first, best = None, None
+    for name, kw, thr in _cpu_modes(cores)[:2]:
+        torch.set_num_threads(thr)
+        torch_port.frontend_torch(wav[:4], lens[:4], weights, **kw)                 # thread pools, FFT plans
+        t0 = time.perf_counter()
+        torch_port.frontend_torch(wav[:n_sample], lens[:n_sample], weights, **kw)
+        dt = time.perf_counter() - t0
+        if first is None or dt < first:
+            first, best = dt, (name, kw, thr)
+    name, kw, thr = best
+    torch.set_num_threads(thr)
     # EXACTLY K timed steps (and W warm-ups); each step is a bounded sample of the workload, sized so that the whole
     # run stays within about two minutes of CPU time: the first n utterances of the batch, all host threads.
     budget = 120.0
@@ -214,25 +262,133 @@ def run_reference(args, rank, world):
     w, l = wav[:n_sample], lens[:n_sample]
     audio_s = float(l.sum()) / SAMPLE_RATE
     for _ in range(warm):
-        torch_port.frontend_torch(w, l, weights)
+        torch_port.frontend_torch(w, l, weights, **kw)
     steps = args.steps
     t0 = time.perf_counter()
     for _ in range(steps):
-        torch_port.frontend_torch(w, l, weights)
+        torch_port.frontend_torch(w, l, weights, **kw)
     dt = (time.perf_counter() - t0) / steps
     val = audio_s / dt
+    sample = (f"each step = first {n_sample} of {args.batch} utterances ({audio_s:.0f} audio-s), sized so that K steps + W "
+              f"warm-ups take about two minutes of CPU time at most; mode {name} ({cores} host threads)")
     line = {
         "impl": "reference", "metric": "audio-seconds/s, log-mel + conv1d subsampling", "value": val,
         "unit": "audio-seconds/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"each step = first {n_sample} of {args.batch} utterances ({audio_s:.0f} audio-s)",
-                   "note": "the per-step sample is sized so that K steps + W warm-ups take about two minutes of CPU time at most"},
-        "cpu_baseline": {"value": val, "unit": "audio-seconds/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"first {n_sample} utterances per step; torch CPU restatement of the TensorFlow path "
-                                   "(oracle/torch_port.py), all host threads"},
+        "config": common_config(args.batch),
+        "sample": sample,
+        "cpu_baseline": {"value": val, "unit": "audio-seconds/s", "cores": cores, "kind": "port", "mode": name,
+                         "sample": sample + "; torch CPU restatement of the TensorFlow path (oracle/torch_port.py)"},
         "e2e": {"value": val, "unit": "audio-seconds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json configs[1], [3], [4]: CUDA-event numbers beside the headline (configs[2])
+# ------------------------------------------------------------------------------------------
+def measure_configs(fe, dev, rank, world, dist, weights):
+    """configs[1]: log-mel only, 64 x 10 s, on every GPU (per-GPU figure from the slowest rank).
+    configs[3]: 1024 x 30 s log-mel + subsampling, STRONG split 1024/N per rank.
+    configs[4]: corner and centre points of the length x batch sweep, strong split of the batch over the ranks.
+    Waveforms are made on the device (eight seeded 'tilt' utterances tiled with per-utterance scale factors: making
+    4096 x 30 s on the host would take minutes); every point runs as one CUDA-graph replay per step (the launch mode of
+    the headline), CUDA events around >= 20 ms of back-to-back steps after two warm-ups, max over ranks."""
+    import torch
+    import telugu_asr_b200 as tasr
+    from telugu_asr_b200.synth import make_waveforms
+    peak, _ = measured_peak()
+    base_np, _ = make_waveforms([480000] * 8, seed=3, dist="tilt")
+    base = torch.from_numpy(base_np).to(dev)
+
+    def batch_of(n_utt, n_samples, first):
+        idx = (torch.arange(n_utt, device=dev) + first)
+        w = base[idx % 8, :n_samples] * (1.0 - 0.002 * (idx % 17).to(torch.float32))[:, None]
+        return w.contiguous(), torch.full((n_utt,), n_samples, dtype=torch.int32, device=dev)
+
+    def reduce_max(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def time_steps(fn, sync):
+        for _ in range(2):
+            fn()
+        sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); sync()
+        n = int(min(200, max(3, 20.0 / max(a.elapsed_time(b), 1e-3))))
+        if dist is not None:
+            tn = torch.tensor([n], dtype=torch.int64, device=dev)
+            dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+            n = int(tn[0])
+            dist.barrier()
+        sync()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        sync()
+        return a.elapsed_time(b) / n, n
+
+    sync = torch.cuda.synchronize
+    out = {}
+    # configs[1] -- the reference-signature featurizer (two passes: peak, then log-mel in the reference's op order)
+    feat = fe.featurizer
+    w, l = batch_of(64, 160000, 0)
+    fbuf = torch.empty((64, 998, 80, 1), dtype=torch.float32, device=dev)
+    ms, n = time_steps(lambda: feat.featurize_batch(w, l, out=fbuf, t_max=998), sync)
+    ms = reduce_max(ms)
+    alg = 64 * (4 * 160000 + 320 * 998)
+    out["configs[1]"] = {"workload": "log-mel only, 64 x 10 s per GPU, SpeechFeaturizer two-pass path (absmax + log-mel kernel)",
+                         "ms_per_step": ms, "steps": n, "audio_s_per_s_per_gpu": 640.0 / (ms * 1e-3),
+                         "algorithmic_bytes": alg, "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak,
+                         "note": "61 MB per step: the batch stays L2-resident between steps (126 MB L2), stated not flushed"}
+    del fbuf
+
+    def frontend_point(total_utt, seconds):
+        """total_utt utterances of `seconds` s split over the ranks (rank r takes a contiguous block)."""
+        per = total_utt // world + (1 if rank < total_utt % world else 0)
+        first = rank * (total_utt // world) + min(rank, total_utt % world)
+        n_s = 16000 * seconds
+        ms_local = 0.0
+        nsteps = 0
+        if per > 0:
+            w_, l_ = batch_of(per, n_s, first)
+            cap_ = tasr.CapturedFrontEnd(fe, per, n_s, dev)
+            cap_.load(w_, l_)
+            del w_
+            sync()
+        if dist is None:
+            ms_local, nsteps = time_steps(cap_.replay, sync)
+        else:
+            # every rank must take part in the collectives inside time_steps, with or without work
+            ms_local, nsteps = time_steps(cap_.replay if per > 0 else (lambda: None), sync)
+            if per == 0:
+                ms_local = 0.0
+        ms_ = reduce_max(ms_local)
+        if per > 0:
+            del cap_
+        torch.cuda.empty_cache()
+        T = 1 + (n_s - 400) // 160
+        t3 = T
+        for _ in range(3):
+            t3 = (t3 - 9) // 2 + 1
+        alg_ = total_utt * (4 * n_s + 4 * 192 * t3 + 4 * t3)
+        return {"utterances": total_utt, "seconds_each": seconds, "ms_per_step": ms_, "steps": nsteps,
+                "audio_s_per_s": total_utt * seconds / (ms_ * 1e-3), "audio_s_per_s_per_gpu": total_utt * seconds / (ms_ * 1e-3) / world,
+                "pipeline_hbm_frac": alg_ / world / (ms_ * 1e-3) / 1e9 / peak}
+
+    out["configs[3]"] = dict(frontend_point(1024, 30), workload=f"log-mel + subsampling, 1024 x 30 s, strong split {1024 // world} per GPU over {world} GPU(s)",
+                             scaling="strong")
+    pts = []
+    for seconds, total in ((1, 1), (1, 4096), (30, 1), (30, 4096), (10, 256)):
+        pts.append(frontend_point(total, seconds))
+    out["configs[4]"] = {"workload": f"length x batch sweep corners + centre, batch split over {world} GPU(s) (strong), vs cpu_baseline",
+                         "points": pts}
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -320,13 +476,28 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------------
+    # The clock sampler runs over a pre-roll, the timed region and a post-roll of the SAME steps (>= 30 ms of load on
+    # either side): K steps alone can be a few milliseconds, less than one NVML sample.
     for _ in range(args.warmup):
         out = step()
     barrier()
+    t_probe0 = time.perf_counter()
+    for _ in range(8):
+        out = step()
+    if cap is not None:
+        cap.join()
+    torch.cuda.synchronize()
+    est_ms = max(1e-3, (time.perf_counter() - t_probe0) * 1e3 / 8)
+    roll = int(min(400, max(4, 30.0 / est_ms)))
     sampler = ClockSampler(local_rank)
-    l0 = lib.tasr_launch_count()
     barrier()
     sampler.start()
+    for _ in range(roll):
+        out = step()
+    if cap is not None:
+        cap.join()
+    l0 = lib.tasr_launch_count()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     if cap is not None:
@@ -336,9 +507,14 @@ def main():
     if cap is not None:
         cap.join()                      # ... and e1 is recorded after all of them
     e1.record()
+    launches = int(lib.tasr_launch_count() - l0)
+    for _ in range(roll):
+        step()
+    if cap is not None:
+        cap.join()
     barrier()
     clocks = sampler.stop()
-    launches = int(lib.tasr_launch_count() - l0)
+    clocks["window"] = f"{roll} untimed steps + the {args.steps} timed steps + {roll} untimed steps, sampled every 4 ms"
     if cap is not None:
         launches = cap.kernels_per_replay * args.steps      # replayed kernels do not pass through the C ABI counter
     ms_total = e0.elapsed_time(e1)
@@ -422,6 +598,11 @@ def main():
     barrier()
     pad_ms = p0.elapsed_time(p1) / pad_steps
 
+    # ---- BASELINE.json configs[1], [3], [4] (outside the headline timed region, like `stages`) -----------------
+    configs = None
+    if not args.no_configs:
+        configs = measure_configs(fe, dev, rank, world, dist if world > 1 else None, weights)
+
     # ---- validation (outside every timed region): NCCL gathers results, nothing on the data path -----
     # Every rank runs a small COMMON batch (same seed) and its own shard of a split batch; the per-utterance
     # checksums (integer sums of the float bit patterns) and lengths are all_gathered to every rank, and rank 0
@@ -473,17 +654,7 @@ def main():
         # each valid log-mel row once (4*N + 4*80*T per utterance)
         T = np.maximum(0, 1 + (lens_np.astype(np.int64) - 400) // 160)
         alg_bytes = float((4 * lens_np.astype(np.int64) + 320 * T).sum())
-        k_ms = stage_us.get("logmel_kernel", float("nan")) * 1e-3
         peak, peak_src = measured_peak()
-        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        traffic, ncu_lm, tj = None, None, {}
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                tj = json.load(fh)
-            ncu_lm = next((v for k, v in tj.items() if k.startswith("logmel_kernel") and isinstance(v, dict)), None)
-            traffic = ncu_lm.get("dram_bytes_per_launch") if ncu_lm else None
-        except Exception:
-            pass
         # per-stage algorithmic bytes: valid samples / valid rows only for the ragged stages
         nvalid = [T]
         for _ in range(3):
@@ -495,16 +666,38 @@ def main():
         for i in range(3):   # x read once where valid + y written once (lean intermediates: where valid; else the whole padded tensor)
             rows_out = int(nvalid[i + 1].sum()) if (lean and i < 2) else args.batch * t_pad[i + 1]
             stage_bytes[f"sepconv_layer{i + 1}"] = float(4 * (int(nvalid[i].sum()) * ch[i] + rows_out * ch[i + 1]))
-        stages = {k: {"us": round(v, 1), "gbs": (round(stage_bytes[k] / (v * 1e-6) / 1e9, 1) if k in stage_bytes else None)}
+        for k in list(stage_us):
+            if k.startswith("logmel") and k not in stage_bytes:
+                stage_bytes[k] = alg_bytes
+        stages = {k: {"us": round(v, 1), "gbs": (round(stage_bytes[k] / (v * 1e-6) / 1e9, 1) if k in stage_bytes else None),
+                      "hbm_frac": (round(stage_bytes[k] / (v * 1e-6) / 1e9 / peak, 3) if k in stage_bytes else None)}
                   for k, v in stage_us.items()}
+        # the dominant kernel = the stage with the largest CUDA-event time
+        dom = max((k for k in stage_us if k in stage_bytes), key=lambda k: stage_us[k])
+        k_ms = stage_us[dom] * 1e-3
+        dom_bytes = stage_bytes[dom]
+        achieved = dom_bytes / (k_ms * 1e-3) / 1e9
+        traffic, ncu_lm, tj = None, None, {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                tj = json.load(fh)
+            ncu_lm = next((v for k, v in tj.items() if k.startswith(dom) and isinstance(v, dict)), None)
+            traffic = ncu_lm.get("dram_bytes_per_launch") if ncu_lm else None
+        except Exception:
+            pass
+        # the whole step against the contract of SURVEY.md 8(d): the waveform read once, [B,T3,192] + mask written once
+        t3 = nvalid[3]
+        pipe_bytes = float((4 * lens_np.astype(np.int64) + 4 * 192 * t3 + 4 * t3).sum())
+        ms_step = ms_total_max / args.steps
         line = {
             "metric": "audio-seconds/s, log-mel + conv1d subsampling", "value": value, "unit": "audio-seconds/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "audio_seconds_per_step_per_gpu": audio_s,
-                       "distribution": "AR(1) rho=0.97 'tilt', peak 0.5, k/32768, seeds 2+rank",
+            "config": common_config(args.batch),
+            "implementation": {
+                       "audio_seconds_per_step_per_gpu": audio_s,
                        "pointwise_math": math_mode + (" (tcgen05 kind::tf32, fp32 accumulate)" if math_mode == "tf32" else " (CUDA-core FMA)"),
-                       "l2": "inputs larger than L2: 246 MB padded waveforms (128 MB of samples read) per step and two steps in flight vs 126 MB L2; no flush needed",
+                       "logmel_math": getattr(fe.featurizer, "logmel_math_used", "fp32 CUDA cores"),
                        "parallelism": f"dp{world} by utterance, no data-path collective",
                        "featurizer": ("single pass: the log-mel kernel finds max|x| while it stages the samples and the first separable conv "
                                       "applies 2 log(gain) and the floor (float32-rounding differences only, tests/test_gpu_parity.py); "
@@ -517,17 +710,24 @@ def main():
                                   "(telugu_asr_b200.InterleavedFrontEnd); roofline.kernel_ms and `stages` are CUDA-event times "
                                   "of the same kernels launched one by one on one stream right after the timed region")
                                  if cap is not None else (graph_note or "kernel-by-kernel launches")},
-            "roofline": {"bound": "hbm", "kernel": "logmel_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": k_ms,
+                         # the whole step against SURVEY.md 8(d)'s pipeline contract (waveform in, encoder input + mask out)
+                         "pipeline_algorithmic_bytes_per_step": pipe_bytes,
+                         "pipeline_achieved": pipe_bytes / (ms_step * 1e-3) / 1e9,
+                         "pipeline_frac": pipe_bytes / (ms_step * 1e-3) / 1e9 / peak,
                          # share of the step's kernel time (sum of the single-stream stage times: comparable with the ncu
                          # launch list, which serialises the kernels); the timed step overlaps two batches, so kernel_ms
                          # divided by ms_per_step would overstate it
                          "kernel_share_of_step": (k_ms * 1e3) / max(sum(stage_us.values()), 1e-9),
                          "kernel_ms_over_ms_per_step": k_ms / (ms_total / args.steps),
-                         "ncu": ({"source": tj.get("source"), **{kk: ncu_lm.get(kk) for kk in ("dram_pct", "issue_active_pct", "fma_pipe_pct", "warp_instructions", "registers", "warps_active_pct")}}
+                         "ncu": ({"source": tj.get("source"), **{kk: ncu_lm.get(kk) for kk in ("dram_pct", "issue_active_pct", "fma_pipe_pct", "tensor_pipe_pct", "warp_instructions", "registers", "warps_active_pct")}}
                                  if ncu_lm else None),
-                         "note": "HBM is the contract bound (SURVEY.md 8d: the waveform read once, the features written once — the kernel now does exactly that, it finds max|x| itself); it is latency-bound at 16 resident warps/SM (issue / FMA-pipe / DRAM utilisation in roofline.ncu; variants with 31 % fewer instructions or with the global loads hidden take the same time or longer), see DESIGN.md 4.2; kernel_ms is its single-stream time, the step overlaps two batches"},
+                         "note": "frac = the dominant kernel's algorithmic bytes (SURVEY.md 8d: what it must read and write once) / its "
+                                 "CUDA-event time / the measured copy bandwidth; pipeline_frac = the same for the whole step against the "
+                                 "fused contract (waveform read once, encoder input + mask written once: 73.6 kB per audio-second); "
+                                 "kernel_ms is the kernel's single-stream time, the timed step overlaps two batches; see DESIGN.md 4"},
             "e2e": {"value": e2e_val, "unit": "audio-seconds/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps, "gpu_launches": e2e_launches,
                     "matches_device_resident_result": e2e_ok, "windows": e2e_windows,
@@ -539,6 +739,7 @@ def main():
                     "f32_padded_single_stream": {"value": audio_s / (pad_ms * 1e-3), "ms_per_step": pad_ms,
                                                  "h2d_bytes_per_step": int(pb.h2d_bytes), "note": "rank 0; padded float32 [B,N_max] H2D, no overlap"}},
             "stages": stages,
+            "configs": configs,
             "validation": validation,
             "gpu_launches": int(float(tsum[5])) if world > 1 else launches,
             "clocks": clocks,

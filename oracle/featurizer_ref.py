@@ -194,11 +194,18 @@ def _stft_power(y: np.ndarray, p: FeatParams, dtype) -> np.ndarray:
     nfft = p.fft_length
     if fr.shape[0] == 0:
         return np.zeros((0, nfft // 2 + 1), dtype=dtype)
-    X = np.fft.rfft(fr, n=nfft, axis=-1)
     if dtype == np.float32:
-        X = X.astype(np.complex64)
+        # A float32 rfft op (TF: Eigen TensorFFT on CPU, cuFFT on GPU) runs its butterflies in float32.  numpy's
+        # np.fft.rfft does NOT: on float32 input it returns the float64 transform rounded once to complex64 (numpy 2.3:
+        # bit-identical, relative rms error 2.5e-8 = pure output rounding), which made the float32 "band" of round 1
+        # ~4x tighter than any genuine float32 FFT.  scipy.fft (pocketfft instantiated for float) computes in single
+        # precision: 1.0e-7 relative rms, the same as torch.fft.rfft / MKL (tests/test_oracle_featurizer.py pins both).
+        import scipy.fft
+        X = scipy.fft.rfft(np.ascontiguousarray(fr, dtype=np.float32), n=nfft, axis=-1)
+        assert X.dtype == np.complex64
         mag = np.abs(X).astype(np.float32)       # tf.abs(complex64) -> float32
         return np.square(mag).astype(np.float32)  # tf.square
+    X = np.fft.rfft(fr, n=nfft, axis=-1)
     mag = np.abs(X)
     return np.square(mag)
 

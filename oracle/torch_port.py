@@ -65,10 +65,39 @@ def subsample_torch(feat: torch.Tensor, n_frames: torch.Tensor, weights, activat
     return h.permute(0, 2, 1).contiguous(), mask, len3
 
 
-def frontend_torch(wav: np.ndarray, lengths: np.ndarray, weights, p: FeatParams | None = None):
-    """The whole reference-style CPU pass over one padded batch."""
+_POOLS = {}
+
+
+def featurize_many_torch(wav: np.ndarray, lengths: np.ndarray, p: FeatParams | None = None, workers: int = 1):
+    """The per-utterance featurizer calls of one batch.  workers > 1 runs them on a thread pool, one utterance per task,
+    the way the reference's tf.data pipeline does (src/dataset.py:227: map(..., num_parallel_calls=AUTOTUNE)); torch
+    releases the GIL inside its kernels, so the calls really overlap.  The caller sets torch's intra-op thread count
+    (1 when the pool already covers the cores)."""
     p = p or yaml_params()
     xs = torch.from_numpy(wav)
-    feats = [logmel_torch(xs[b, : int(lengths[b])], p) for b in range(wav.shape[0])]
+    items = [xs[b, : int(lengths[b])] for b in range(wav.shape[0])]
+    if workers <= 1:
+        return [logmel_torch(x, p) for x in items]
+    from concurrent.futures import ThreadPoolExecutor
+    pool = _POOLS.get(workers)
+    if pool is None:
+        pool = _POOLS[workers] = ThreadPoolExecutor(max_workers=workers)
+    return list(pool.map(lambda x: logmel_torch(x, p), items))
+
+
+def frontend_torch(wav: np.ndarray, lengths: np.ndarray, weights, p: FeatParams | None = None, workers: int = 1,
+                   conv_threads: int | None = None):
+    """The whole reference-style CPU pass over one padded batch: per-utterance featurizer calls (optionally `workers` at
+    a time, each single-threaded), zero-pad collate, then the three separable convs on the padded batch with
+    `conv_threads` intra-op threads (default: leave torch's setting alone)."""
+    if workers > 1:
+        prev = torch.get_num_threads()
+        torch.set_num_threads(1)
+        try:
+            feats = featurize_many_torch(wav, lengths, p, workers)
+        finally:
+            torch.set_num_threads(conv_threads or prev)
+    else:
+        feats = featurize_many_torch(wav, lengths, p, 1)
     feat, n = collate_torch(feats)
     return subsample_torch(feat, n, weights) + (feat, n)

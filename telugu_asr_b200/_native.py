@@ -102,9 +102,10 @@ def lib() -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            from . import build as _build
-            _build.build()
+        # always through build(): it returns at once when the source digest matches the stamp, and rebuilds a stale
+        # library (a source, header or the generated mel_geometry.inc changed) instead of silently loading it
+        from . import build as _build
+        _build.build()
         try:
             handle = C.CDLL(LIB_PATH)
         except OSError as e:

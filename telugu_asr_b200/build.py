@@ -37,7 +37,7 @@ def _digest() -> str:
     h = hashlib.sha256()
     h.update(" ".join(NVCC_FLAGS).encode())
     files = [os.path.join(CSRC, s) for s in SOURCES]
-    files += [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
+    files += [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h", ".inc"))]
     files.append(os.path.join(HERE, "..", "include", "tasr.h"))
     for f in files:
         with open(f, "rb") as fh:

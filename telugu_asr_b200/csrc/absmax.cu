@@ -27,7 +27,10 @@ absmax_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, in
   if (start >= n) return;
   const float* row = wav + (size_t)b * row_stride;
   const int end = min(n, start + kChunk);
-  float m = 0.0f;
+  // The maximum is taken over the BIT PATTERNS of |x| as unsigned integers: they order like the values for finite
+  // samples and put a NaN (0x7fc00000 and up) above +inf, so a NaN sample makes the peak NaN exactly like
+  // tf.reduce_max(tf.abs(x)) (src/speech_featurizer.py:70) - fmaxf would silently drop it.
+  unsigned m = 0u;
   // row is 16-byte aligned and start is a multiple of 4 -> float4 loads; tail handled scalar.
   const int nvec = (end - start) >> 2;
   const float4* v4 = reinterpret_cast<const float4*>(row + start);
@@ -39,18 +42,16 @@ absmax_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, in
   }
 #pragma unroll
   for (int i = 0; i < kVecPerThread; ++i)
-    m = fmaxf(m, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
-  for (int i = start + (nvec << 2) + threadIdx.x; i < end; i += kThreads) m = fmaxf(m, fabsf(row[i]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  __shared__ float sm[kThreads / 32];
+    m = max(m, max(max(abs_bits(v[i].x), abs_bits(v[i].y)), max(abs_bits(v[i].z), abs_bits(v[i].w))));
+  for (int i = start + (nvec << 2) + threadIdx.x; i < end; i += kThreads) m = max(m, abs_bits(row[i]));
+  m = __reduce_max_sync(0xffffffffu, m);
+  __shared__ unsigned sm[kThreads / 32];
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x < 32) {
-    m = (threadIdx.x < kThreads / 32) ? sm[threadIdx.x] : 0.0f;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (threadIdx.x == 0) atomicMax(reinterpret_cast<int*>(peak + b), __float_as_int(m));
+    m = (threadIdx.x < kThreads / 32) ? sm[threadIdx.x] : 0u;
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned*>(peak + b), m);
   }
 }
 

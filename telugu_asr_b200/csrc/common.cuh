@@ -48,6 +48,10 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int sm_count();  // SMs of the current device (cached per device)
 
+// |x| as its bit pattern.  Unsigned-integer max over these orders finite values like fmaxf does and ranks a NaN above
+// +inf, so max|x| reductions propagate NaN the way tf.reduce_max(tf.abs(x)) does (src/speech_featurizer.py:70).
+__device__ __forceinline__ unsigned abs_bits(float x) { return __float_as_uint(x) & 0x7fffffffu; }
+
 // Fixed front-end geometry the kernels are specialised for (config/model.yaml:1-17).
 constexpr int kFrameLen = 400;
 constexpr int kFrameStep = 160;

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(MAXT, MINB) conv2d_first_kernel(const float* _
     const float g = __fdiv_rn(1.0f, __fadd_rn(in_peak[b], 1e-9f));
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(g));
     gc = in_scale2 * lg;
+    if (gc != gc) in_floor = gc;   // NaN peak: the utterance's features are NaN (fmaxf alone would drop it)
   }
   const float* xb = x + (size_t)b * T * W;
   for (int k = threadIdx.x; k < (2 * kC1Rows + 1) * SW; k += blockDim.x) {

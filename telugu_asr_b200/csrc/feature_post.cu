@@ -133,6 +133,7 @@ __global__ void apply_gain_kernel(float* __restrict__ feat, const int32_t* __res
   const float g = __fdiv_rn(1.0f, __fadd_rn(peak[b], 1e-9f));
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(g));
   const float c = scale2 * lg;
+  if (c != c) floor_ = c;     // a NaN peak (a NaN sample) makes the whole utterance NaN, like the reference; fmaxf alone would drop it
   float* row = feat + (size_t)b * T_max * F;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) row[i] = fmaxf(row[i] + c, floor_);
 }

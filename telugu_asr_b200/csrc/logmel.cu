@@ -253,20 +253,20 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
         // Single pass: max|x| of the samples this tile stages (slots beyond `lim` hold zeros); the tile that holds the
         // utterance's last frame also takes the samples no frame covers, [s0+count, n).  Non-negative floats order like
         // their bit patterns, so the warp maximum is one integer REDUX and the merge one atomicMax per warp.
-        float m = 0.0f;
+        unsigned m = 0u;   // integer max over the bit patterns of |x|: finite values order like floats, a NaN sample wins
 #pragma unroll
         for (int u = 0; u < kWavSlots; ++u)
-          m = fmaxf(fmaxf(m, fmaxf(fabsf(x[u].x), fabsf(x[u].y))), fmaxf(fabsf(x[u].z), fabsf(x[u].w)));
+          m = max(max(m, max(abs_bits(x[u].x), abs_bits(x[u].y))), max(abs_bits(x[u].z), abs_bits(x[u].w)));
         if (f0 + nvalid >= Tb) {
           for (int i = s0 + count + 4 * tid; i < n; i += 4 * kThreads) {
             const float4 t4 = *reinterpret_cast<const float4*>(row + i);
-            m = fmaxf(m, fabsf(t4.x));
-            if (i + 1 < n) m = fmaxf(m, fabsf(t4.y));
-            if (i + 2 < n) m = fmaxf(m, fabsf(t4.z));
-            if (i + 3 < n) m = fmaxf(m, fabsf(t4.w));
+            m = max(m, abs_bits(t4.x));
+            if (i + 1 < n) m = max(m, abs_bits(t4.y));
+            if (i + 2 < n) m = max(m, abs_bits(t4.z));
+            if (i + 3 < n) m = max(m, abs_bits(t4.w));
           }
         }
-        const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+        const unsigned mb = __reduce_max_sync(0xffffffffu, m);
         if (lane == 0 && mb != 0u) atomicMax(reinterpret_cast<unsigned*>(a.peak_out) + b, mb);
       }
 #pragma unroll

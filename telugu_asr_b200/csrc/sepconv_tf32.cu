@@ -144,12 +144,13 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
       for (int k = 0; k < 9; ++k) w[k] = cok ? __ldg(a.dw + k * C_in + c0 + lane) : 0.0f;
     }
     if (fix) {                            // rows of the data get the gain and the floor; padding rows stay 0.0
+      const float fl = (gc == gc) ? a.in_floor : gc;   // NaN peak -> NaN rows (fmaxf alone would drop the NaN)
       if (r0 + kWin <= cf) {
 #pragma unroll
-        for (int i = 0; i < kWin; ++i) v[i] = fmaxf(v[i] + gc, a.in_floor);
+        for (int i = 0; i < kWin; ++i) v[i] = fmaxf(v[i] + gc, fl);
       } else {
 #pragma unroll
-        for (int i = 0; i < kWin; ++i) v[i] = (r0 + i < cf) ? fmaxf(v[i] + gc, a.in_floor) : v[i];
+        for (int i = 0; i < kWin; ++i) v[i] = (r0 + i < cf) ? fmaxf(v[i] + gc, fl) : v[i];
       }
     }
     }

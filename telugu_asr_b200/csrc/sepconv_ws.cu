@@ -277,13 +277,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const __grid_
           for (int i = 0; i < kWinWs; ++i) v[i] = xw[i * kKC];
           if (a.in_peak != nullptr) {      // rows of the data get the deferred gain and the floor; padding rows stay 0.0
             const float gc = list_gc[k];
+            const float fl = (gc == gc) ? a.in_floor : gc;   // NaN peak -> NaN rows (fmaxf alone would drop the NaN)
             const int cf = list_cf[k];
             if (r0 + kWinWs <= cf) {
 #pragma unroll
-              for (int i = 0; i < kWinWs; ++i) v[i] = fmaxf(v[i] + gc, a.in_floor);
+              for (int i = 0; i < kWinWs; ++i) v[i] = fmaxf(v[i] + gc, fl);
             } else {
 #pragma unroll
-              for (int i = 0; i < kWinWs; ++i) v[i] = (r0 + i < cf) ? fmaxf(v[i] + gc, a.in_floor) : v[i];
+              for (int i = 0; i < kWinWs; ++i) v[i] = (r0 + i < cf) ? fmaxf(v[i] + gc, fl) : v[i];
             }
           }
         }

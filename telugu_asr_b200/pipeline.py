@@ -176,8 +176,10 @@ class FrontEndPipeline:
                 self.ev_ready[slot].record(self.s_in)
             comp.wait_event(self.ev_ready[slot])
             wav, lens = pb.unpack()
-            self.ev_free[slot].record(comp)
             out, mask, len3 = self.fe(wav, lens, max_length=pb.max_len)
+            # `lens` IS the slot's device length buffer and every kernel of the batch reads it, so the slot is free for
+            # the next H2D only when the whole front end has run (not right after the unpack)
+            self.ev_free[slot].record(comp)
             self.ev_comp[slot].record(comp)
             h_out, h_mask, h_len = self._host_buffers(slot, out, mask, len3)
             self.s_out.wait_event(self.ev_comp[slot])

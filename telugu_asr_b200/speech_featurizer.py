@@ -254,8 +254,9 @@ class SpeechFeaturizer:
         B, n_max = wav.shape
         if wav.stride(1) != 1 and n_max > 1:
             wav = wav.contiguous()
-        row_stride = wav.stride(0) if B > 1 else -(-max(n_max, 0) // 4) * 4   # one row: stride is never used
-        if (row_stride % 4) or (wav.data_ptr() % 16):
+        row_stride = wav.stride(0) if B > 1 else max(n_max, 0)   # one row: the stride only has to cover the row
+        if (row_stride % 4) or (wav.data_ptr() % 16):   # (a single row of n_max % 4 != 0 samples is padded too: the kernels
+            # read whole 16-byte vectors up to the row's end)
             # keep rows 16-byte aligned for the 128-bit loads (costs one copy; pad N_max to a
             # multiple of 4 upstream to avoid it)
             n_pad = -(-n_max // 4) * 4

@@ -2,14 +2,17 @@
 (via the ctypes binding the Python mirror uses), against the CPU oracle on the same seeded inputs
 and against the committed fixtures under tests/golden/.
 
-Tolerances (BASELINE.json north_star): log-mel max-abs <= 1e-4 against the float64 oracle on the
-primary "tilt" distribution.  On the stress distributions (white noise, tone+noise) the float32
-noise floor itself sits at that level (SURVEY.md hard part 1: pocketfft float32 vs float64 is
-5e-5..1.2e-3 there), so the bound is 4x the float32 oracle's own band: the kernel's packed
-even/odd real FFT measures ~3x pocketfft's float32 noise on white noise (tools/fft_scheme_proto.py,
-DESIGN.md "Numerics").  Subsampled features:
-max-abs error / max-abs reference <= 1e-3 (TF32) and <= 2e-5 (FP32 path).  Frame counts, conv
-lengths and masks: bit-exact."""
+Tolerances (BASELINE.json north_star), none of them fitted to a kernel:
+  * log-mel, primary "tilt" distribution: max-abs <= 1e-4 against the float64 oracle, EVERY value, at every size
+    (configs[1], configs[2] full size included; no outlier quota);
+  * log-mel, stress distributions (white noise, tone+noise): a float32 evaluation of the reference's own op sequence is
+    itself further than 1e-4 from float64 there (its pre-emphasis / window / FFT roundings land on near-cancelled
+    low mel bins), so the bound is max(1e-4, STRESS_BAND x the float32 oracle's own distance from float64 on the same
+    input), STRESS_BAND = 2.5.  The float32 oracle runs a genuine single-precision FFT (scipy pocketfft<float>,
+    pinned against torch.fft in tests/test_oracle_featurizer.py); round 1 used np.fft.rfft, which computes in double
+    and returned a band ~4x tighter than any float32 FFT can be (oracle/featurizer_ref.py:_stft_power);
+  * subsampled features: max-abs error / max-abs reference <= 1e-3 (TF32) and <= 2e-5 (FP32 path);
+  * frame counts, conv lengths and masks: bit-exact."""
 import ctypes
 import os
 
@@ -24,6 +27,7 @@ from telugu_asr_b200 import _native
 pytestmark = pytest.mark.gpu
 
 LOGMEL_TOL = 1e-4
+STRESS_BAND = 2.5
 SUB_TOL_TF32 = 1e-3
 SUB_TOL_FP32 = 2e-5
 
@@ -43,31 +47,22 @@ def run_logmel(feat, wav, ln, dev):
     return out.cpu().numpy(), nf.cpu().numpy()
 
 
-def band_tol(wav, ln, ref64):
-    f32, _ = oracle.logmel_batch_ref(wav, ln, dtype=np.float32)
-    return max(LOGMEL_TOL, 4.0 * float(np.abs(f32 - ref64).max()))
+def band_tol(wav, ln, ref64, p=None):
+    f32, _ = oracle.logmel_batch_ref(wav, ln, p, dtype=np.float32) if p is not None else oracle.logmel_batch_ref(wav, ln, dtype=np.float32)
+    return max(LOGMEL_TOL, STRESS_BAND * float(np.abs(f32 - ref64).max()))
 
 
 def assert_logmel_parity(out, wav, ln):
-    """Per utterance: max-abs error vs the float64 oracle <= max(1e-4, 4 x the float32 oracle's own
-    band on that utterance); over everything: fewer than 1e-6 of the values outside 1e-4.  (On 30M
-    values a handful land on near-cancelled low mel bins, ~1e-9 power, where pocketfft-float32 is
-    itself 1e-3 off float64 — measured in tests/diag_logmel.py.)"""
-    n_bad = n_all = 0
+    """Primary distribution, any size: every value within 1e-4 of the float64 oracle.  Returns the worst error."""
     worst = 0.0
     for b in range(wav.shape[0]):
         r64 = oracle.logmel_ref(wav[b, : ln[b]], dtype=np.float64)
         T = r64.shape[0]
         if T == 0:
             continue
-        e = np.abs(out[b, :T, :, 0] - r64)
-        n_bad += int((e > LOGMEL_TOL).sum())
-        n_all += e.size
-        if e.max() > LOGMEL_TOL:
-            r32 = oracle.logmel_ref(wav[b, : ln[b]], dtype=np.float32)
-            assert e.max() <= 4.0 * np.abs(r32 - r64).max(), (b, e.max(), np.abs(r32 - r64).max())
-        worst = max(worst, float(e.max()))
-    assert n_bad <= max(1, int(1e-6 * n_all)), (n_bad, n_all)
+        e = float(np.abs(out[b, :T, :, 0] - r64).max())
+        assert e <= LOGMEL_TOL, (b, e)
+        worst = max(worst, e)
     return worst
 
 
@@ -380,7 +375,7 @@ def test_logmel_other_filterbank_takes_generic_path(cuda_device):
     ref64, nref = oracle.logmel_batch_ref(wav, ln, p, dtype=np.float64)
     np.testing.assert_array_equal(nf, nref)
     ref32, _ = oracle.logmel_batch_ref(wav, ln, p, dtype=np.float32)
-    tol = max(LOGMEL_TOL * np.log(10.0), 4.0 * float(np.abs(ref32 - ref64).max()))   # natural log: 1e-4 * ln(10)
+    tol = max(LOGMEL_TOL * np.log(10.0), STRESS_BAND * float(np.abs(ref32 - ref64).max()))   # natural log: 1e-4 * ln(10)
     assert np.abs(out - ref64).max() <= tol
     # and the config/model.yaml bank really is on the unrolled path
     lib = _native.lib()
@@ -500,7 +495,7 @@ def test_featurizer_other_modes(cuda_device, name, over):
     np.testing.assert_array_equal(nf, nref)                                    # bit-exact frame counts
     assert [f.get_nframes(int(L)) if L >= (1 if p.pad_end else 400) else 0 for L in lens] == nref.tolist()
     assert out.shape == ref64.shape and np.isfinite(out).all()
-    tol = max(LOGMEL_TOL, 4.0 * float(np.abs(ref32 - ref64).max()))
+    tol = max(LOGMEL_TOL, STRESS_BAND * float(np.abs(ref32 - ref64).max()))
     assert np.abs(out - ref64).max() <= tol, (name, np.abs(out - ref64).max(), tol)
     for b, t in enumerate(nf):
         assert not out[b, t:].any()
@@ -819,21 +814,18 @@ def test_single_pass_featurizer_matches_two_pass(feat, cuda_device, dist):
         if t:
             d = (one[b, :t] - two[b, :t]).abs().max().item()
             assert d <= 2e-5, (b, d)
-    # against the float64 oracle: <= 1e-4 on the primary distribution; on the stress distributions (where the float32
-    # noise floor itself is at that level, see the module docstring) never more than the 2e-5 above worse than the
-    # two-pass kernel on the same utterance, and no more values outside 1e-4 than twice the two-pass kernel's count
-    o, o2 = one.cpu().numpy(), two.cpu().numpy()
-    n_bad = n_bad2 = n_all = 0
+    # against the float64 oracle, the same bound as the two-pass kernel: <= 1e-4 on the primary distribution, every value;
+    # on the stress distributions max(1e-4, STRESS_BAND x the float32 oracle's own band on that utterance)
+    o = one.cpu().numpy()
     for b, t in enumerate(nf.cpu().tolist()):
         if t:
             r64 = oracle.logmel_ref(wav[b, : ln[b]], dtype=np.float64)
-            e1 = np.abs(o[b, :t, :, 0] - r64)
-            e2 = np.abs(o2[b, :t, :, 0] - r64)
-            n_bad += int((e1 > LOGMEL_TOL).sum())
-            n_bad2 += int((e2 > LOGMEL_TOL).sum())
-            n_all += e1.size
-            assert e1.max() <= (LOGMEL_TOL if dist == "tilt" else max(LOGMEL_TOL, e2.max() + 2e-5)), (b, e1.max(), e2.max())
-    assert n_bad <= 2 * n_bad2 + max(1, int(1e-5 * n_all)), (n_bad, n_bad2, n_all)
+            e1 = float(np.abs(o[b, :t, :, 0] - r64).max())
+            tol = LOGMEL_TOL
+            if dist != "tilt":
+                r32 = oracle.logmel_ref(wav[b, : ln[b]], dtype=np.float32)
+                tol = max(LOGMEL_TOL, STRESS_BAND * float(np.abs(r32 - r64).max()))
+            assert e1 <= tol, (b, e1, tol)
 
 
 def test_single_pass_frontend_matches_two_pass_and_oracle(cuda_device):
@@ -1050,3 +1042,101 @@ def test_conformer_front_end_single_pass_matches_two_pass_and_oracle(cuda_device
     ref_out, ref_len = oracle.conv2d_subsample_ref(ref_feat, ref_nf, ws, dtype=np.float64)
     assert np.abs(a.cpu().numpy() - ref_out).max() / np.abs(ref_out).max() <= SUB_TOL_TF32
     np.testing.assert_array_equal(res[True][1].cpu().numpy(), ref_len)
+
+
+def test_bench_default_chain_config4_shape_through_subsampling(cuda_device):
+    """BASELINE.json configs[3] shape (30 s utterances; 128 of them = one GPU's share of the 1024 at 8 GPUs) through the
+    chain bench.py times by default — single pass over the waveform, lean intermediates, persistent warp-specialised
+    convs, one CUDA-graph replay per step on one of two interleaved streams — checked against the oracle THROUGH
+    subsampling on sampled utterances (full length, ragged, one frame, no frame), lengths and mask on all of them."""
+    B, N = 128, 480000
+    lens = np.full(B, N, dtype=np.int32)
+    lens[3], lens[40], lens[77], lens[126] = 240017, 400, 399, 31999
+    base, _ = oracle.make_waveforms([N] * 8, seed=3, dist="tilt")
+    scale = (1.0 - 0.003 * (np.arange(B) % 13)).astype(np.float32)
+    wav = (np.tile(base, (B // 8, 1)) * scale[:, None]).astype(np.float32)
+    for b in (3, 40, 77, 126):
+        wav[b, lens[b]:] = 0.0
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    fe = tasr.FrontEnd(math="tf32")                     # defaults: single_pass, lean_intermediates, ws kernels
+    fe.set_weights(weights, cuda_device)
+    assert fe.single_pass and fe.lean_intermediates
+    il = tasr.InterleavedFrontEnd(fe, B, N, cuda_device, n_streams=2)
+    w, l = gpu(wav, cuda_device), gpu(lens, cuda_device)
+    for i in range(2):
+        il.load(i, w, l)
+    il.fork()
+    outs = [il.replay(i) for i in range(4)]             # both slots, twice
+    il.join()
+    torch.cuda.synchronize()
+    enc, mask, len3 = (t.cpu().numpy() for t in outs[3])
+    assert enc.shape == (B, 368, 192) and mask.shape[0] == B
+    for t in outs[:3]:                                  # every replay of either slot gives the same bits
+        assert torch.equal(t[0], outs[3][0]) and torch.equal(t[2], outs[3][2])
+    nf = np.array([oracle.get_nframes(int(n)) for n in lens], dtype=np.int32)
+    ref_len = oracle.conv_lengths_ref(nf)[-1]
+    np.testing.assert_array_equal(len3, ref_len)
+    np.testing.assert_array_equal(mask[:, : int(ref_len.max())], oracle.lengths_to_padding_mask_ref(ref_len))
+    for b in (0, 3, 40, 77, 126, 127):
+        n, L = int(lens[b]), int(ref_len[b])
+        if L == 0:
+            continue
+        f32, nfb = oracle.logmel_batch_ref(wav[b: b + 1, :n], lens[b: b + 1], dtype=np.float32)
+        ro, _, rl = oracle.subsample_ref(f32, nfb, weights, dtype=np.float64)
+        assert int(rl[-1][0]) == L
+        err = np.abs(enc[b, :L] - ro[0, :L]).max() / np.abs(ro[0, :L]).max()
+        assert err <= SUB_TOL_TF32, (b, err)
+
+
+def test_nan_sample_makes_the_whole_utterance_nan_like_the_reference(feat, cuda_device):
+    """tf.reduce_max(tf.abs(x)) propagates NaN (src/speech_featurizer.py:70): one corrupted sample turns the gain, and
+    with it every feature of THAT utterance, into NaN; the neighbours in the batch are untouched.  Both the two-pass
+    peak kernel and the single-pass peak inside the log-mel kernel reduce bit patterns, not fmaxf."""
+    wav, ln = oracle.make_waveforms([16000, 16000, 8000], seed=9, dist="tilt")
+    clean, _ = run_logmel(feat, wav, ln, cuda_device)
+    wav[1, 12345] = np.nan
+    w, l = gpu(wav, cuda_device), gpu(ln, cuda_device)
+    out, nf = feat(w, l)
+    raw, nf1, gain = feat.featurize_batch(w, l, single_pass=True)
+    one = feat.apply_deferred_gain(raw.clone(), nf1, gain)
+    torch.cuda.synchronize()
+    for o in (out.cpu().numpy(), one.cpu().numpy()):
+        assert np.isnan(o[1, : nf[1]]).all()
+        assert np.isfinite(o[0]).all() and np.isfinite(o[2]).all()
+    np.testing.assert_array_equal(out.cpu().numpy()[0], clean[0])
+    assert torch.isnan(gain.peak[1]) and not torch.isnan(gain.peak[0])
+
+
+def test_eager_pipeline_slot_reuse_keeps_lengths_of_in_flight_batches(cuda_device):
+    """FrontEndPipeline(graph=False), two slots, eight back-to-back submits of batches with DIFFERENT lengths and no
+    host wait in between: a slot's device length buffer is read by every kernel of its batch, so the slot may only be
+    overwritten by the next H2D after the whole front end has run (the event used to be recorded right after
+    the unpack)."""
+    from telugu_asr_b200.synth import draw_lengths, to_pcm16
+    n_max, B = 64000, 24
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    fe = tasr.FrontEnd(math="tf32")
+    fe.set_weights(weights, cuda_device)
+    pipe = tasr.FrontEndPipeline(fe, B, n_max, cuda_device, pcm16=True, slots=2, graph=False)
+    batches, want = [], []
+    for i in range(8):
+        lens = draw_lengths(B, 800, n_max, seed=60 + i)
+        lens[0] = n_max
+        wav, ln = oracle.make_waveforms(lens, seed=60 + i, dist="tilt")
+        batches.append([to_pcm16(wav[b, : ln[b]]) for b in range(B)])
+        o = _call_or_skip(fe, gpu(wav, cuda_device), gpu(ln, cuda_device), max_length=n_max)
+        want.append(tuple(t.cpu() for t in o))
+    torch.cuda.synchronize()
+    # two extra staging sets so that the host never has to wait for a slot: pre-pack everything, then submit in a burst
+    got = []
+    for i, utts in enumerate(batches):
+        pipe.stage(i % 2, utts)
+        tk = pipe.submit(i % 2)
+        got.append(tk)
+        if i >= 1:                                     # collect the previous ticket before its slot is re-staged
+            res = got[i - 1].wait()
+            got[i - 1] = tuple(t.clone() for t in res)
+    got[-1] = tuple(t.clone() for t in got[-1].wait())
+    for i in range(8):
+        for g, w in zip(got[i], want[i]):
+            assert torch.equal(g, w), i

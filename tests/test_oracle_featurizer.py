@@ -71,7 +71,10 @@ def test_mel_matrix_vs_float64_formula_and_torchaudio():
     ref = np.maximum(0.0, np.minimum((bins - lo) / (ce - lo), (hi - bins) / (hi - ce)))
     ref = np.pad(ref, [[1, 0], [0, 0]])
     assert np.abs(W - ref).max() < 5e-5          # float32 op-order noise only
-    torchaudio = pytest.importorskip("torchaudio")
+    try:                                        # torchaudio is not in this image; the HF pin below is the mandatory one
+        import torchaudio
+    except ImportError:
+        return
     fb = torchaudio.functional.melscale_fbanks(257, 0.0, 8000.0, 80, 16000, norm=None, mel_scale="htk").numpy()
     # torchaudio's triangles are linear in Hz, TF's in mel: same supports, weights within 0.5 %
     assert np.abs(fb - W).max() < 5e-3
@@ -132,7 +135,31 @@ def test_silence_floor_and_collate_padding():
     assert np.all(out[0, 4:] == 0.0) and np.all(out[0, :4] == -9.0)
 
 
-@pytest.mark.parametrize("dist,band", [("tilt", 3e-5), ("white", 2e-4), ("half_silence", 3e-5)])
+def test_float32_oracle_runs_a_genuine_float32_fft():
+    """The float32 oracle's FFT stage must compute in single precision, like the reference's TF op does.  numpy's
+    np.fft.rfft on float32 input is the float64 transform rounded once (relative rms error 2.5e-8 = output rounding
+    only) - a band no float32 FFT can live in; scipy.fft (what the oracle uses) and torch.fft (MKL / pocketfft, an
+    independent float32 FFT) both sit at ~1e-7.  Pins which one the oracle uses and that the two agree."""
+    import scipy.fft
+    import torch
+    from oracle import featurizer_ref as fr
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((256, 400)) * fr.hann_periodic(400)).astype(np.float32)
+    ref = np.fft.rfft(x.astype(np.float64), n=512, axis=1)
+    rms = np.sqrt((np.abs(ref) ** 2).mean())
+    err = lambda X: float(np.sqrt((np.abs(X - ref) ** 2).mean()) / rms)
+    e_np = err(np.fft.rfft(x, n=512, axis=1))
+    e_sp = err(scipy.fft.rfft(x, n=512, axis=1))
+    e_th = err(torch.fft.rfft(torch.from_numpy(x), n=512, dim=1).numpy())
+    assert e_np < 4e-8                               # double inside: not a float32 FFT
+    assert 6e-8 < e_sp < 2e-7 and 6e-8 < e_th < 2e-7 and 0.5 < e_sp / e_th < 2.0
+    p = fr.yaml_params()
+    P32 = fr._stft_power(x[0], fr.FeatParams(**{**p.__dict__, "pad_end": False}), np.float32)
+    X1 = scipy.fft.rfft((x[0, :400] * fr.hann_periodic(400)).astype(np.float32), n=512)
+    np.testing.assert_array_equal(P32[0], np.square(np.abs(X1).astype(np.float32)))   # the oracle's spectrum IS scipy's float32 one
+
+
+@pytest.mark.parametrize("dist,band", [("tilt", 3e-5), ("white", 2e-3), ("half_silence", 3e-5)])
 def test_float32_band_vs_float64(dist, band):
     """The error band any float32 implementation of the path lives in (SURVEY.md hard part 1)."""
     wav, ln = oracle.make_waveforms([48000], seed=0, dist=dist)
@@ -188,7 +215,7 @@ def test_logmel_oracle_vs_transformers_audio_utils():
     1e-5 (TF builds the matrix in float32, HF in float64), log-mel within 5e-5 end to end and within 5e-6 when HF's
     chain is handed the oracle's float32-built matrix.  (Normalisation and pre-emphasis are applied to the signal
     first, as src/speech_featurizer.py:68-79 does; HF's own per-frame Kaldi pre-emphasis is a different operation.)"""
-    au = pytest.importorskip("transformers.audio_utils")
+    import transformers.audio_utils as au      # mandatory: this is the oracle's only third-party end-to-end pin
     from oracle import featurizer_ref as fr
     W = fr.htk_mel_matrix_f32()
     fb = au.mel_filter_bank(num_frequency_bins=257, num_mel_filters=80, min_frequency=0.0, max_frequency=8000.0,
