@@ -227,6 +227,9 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
     const int nvalid = min(kTileFrames, Tb - f0);   // >= 1: only valid tiles are enumerated
     float* orow = a.out + ((size_t)b * a.T_max + f0) * kMel;
 
+    // a NaN peak (a NaN sample somewhere in the utterance) makes every feature of the utterance NaN, as in the
+    // reference; fmaxf(NaN, floor) alone would return the floor
+    float floor_b = a.floor_;
     // ---- stage the tile: gain, pre-emphasis (reference float32 op order), to shared --------
     {
       const float* row = a.wav + (size_t)b * a.row_stride;
@@ -235,6 +238,7 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
       const int lim = a.pad_end ? min(count, n - s0) : count;   // samples of the tile that exist
       float g = 1.0f;
       if (a.normalize && a.peak_out == nullptr) g = __fdiv_rn(1.0f, __fadd_rn(a.peak[b], 1e-9f));  // :70
+      if (g != g) floor_b = g;
       const float c = a.preemph;
       float4 x[kWavSlots];
       float xp[kWavSlots];
@@ -364,17 +368,17 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
       const float* Prow = S.P + lane * kPStride;
       float* srow = stage + lane * kOutStride;
       if (a.mode == 1) {   // "spectrogram": log power of the first 80 FFT bins (src/speech_featurizer.py:124-126)
-        for (int k = warp; k < kMel; k += kWarps) srow[k] = lg2_normal(fmaxf(Prow[k], a.floor_)) * a.log_scale;
+        for (int k = warp; k < kMel; k += kWarps) srow[k] = lg2_normal(fmaxf(Prow[k], floor_b)) * a.log_scale;
       } else if (FIXED) {
         switch (warp) {
-          case 0: mel_fixed_group<0>(Prow, mw, srow, a.floor_, a.log_scale); break;
-          case 1: mel_fixed_group<1>(Prow, mw, srow, a.floor_, a.log_scale); break;
-          case 2: mel_fixed_group<2>(Prow, mw, srow, a.floor_, a.log_scale); break;
-          case 3: mel_fixed_group<3>(Prow, mw, srow, a.floor_, a.log_scale); break;
-          case 4: mel_fixed_group<4>(Prow, mw, srow, a.floor_, a.log_scale); break;
-          case 5: mel_fixed_group<5>(Prow, mw, srow, a.floor_, a.log_scale); break;
-          case 6: mel_fixed_group<6>(Prow, mw, srow, a.floor_, a.log_scale); break;
-          default: mel_fixed_group<7>(Prow, mw, srow, a.floor_, a.log_scale); break;
+          case 0: mel_fixed_group<0>(Prow, mw, srow, floor_b, a.log_scale); break;
+          case 1: mel_fixed_group<1>(Prow, mw, srow, floor_b, a.log_scale); break;
+          case 2: mel_fixed_group<2>(Prow, mw, srow, floor_b, a.log_scale); break;
+          case 3: mel_fixed_group<3>(Prow, mw, srow, floor_b, a.log_scale); break;
+          case 4: mel_fixed_group<4>(Prow, mw, srow, floor_b, a.log_scale); break;
+          case 5: mel_fixed_group<5>(Prow, mw, srow, floor_b, a.log_scale); break;
+          case 6: mel_fixed_group<6>(Prow, mw, srow, floor_b, a.log_scale); break;
+          default: mel_fixed_group<7>(Prow, mw, srow, floor_b, a.log_scale); break;
         }
       } else {
 #pragma unroll 1
@@ -390,7 +394,7 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
             acc = fmaf(pp[4 * i + 2], w.z, acc);
             acc = fmaf(pp[4 * i + 3], w.w, acc);
           }
-          srow[m] = lg2_normal(fmaxf(acc, a.floor_)) * a.log_scale;
+          srow[m] = lg2_normal(fmaxf(acc, floor_b)) * a.log_scale;
         }
       }
     }
