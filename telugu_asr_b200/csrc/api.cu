@@ -117,6 +117,12 @@ extern "C" int tasr_featurizer_create(const TasrFeatParams* p, const float* hann
   if (rc == TASR_OK) rc = check_cuda(cudaMemcpy(f->d_tw512, tw512.data(), 256 * sizeof(float2), cudaMemcpyHostToDevice), "copy tw512");
   if (rc == TASR_OK) rc = check_cuda(cudaMemcpy(f->d_band_w, bw.data(), kMelBandMaxW4 * sizeof(float4), cudaMemcpyHostToDevice), "copy band_w");
   if (rc == TASR_OK) rc = check_cuda(cudaMemcpy(f->d_bands, &bands, sizeof(MelBands), cudaMemcpyHostToDevice), "copy bands");
+  if (rc == TASR_OK && f->mel_fixed) {   // operand images of the tensor-core log-mel kernel (logmel_tc.cu)
+    std::vector<unsigned char> img(16384, 0);
+    tasr_logmel_tc_build_dft32(img.data());
+    rc = check_cuda(cudaMalloc(&f->d_dft32, img.size()), "cudaMalloc dft32");
+    if (rc == TASR_OK) rc = check_cuda(cudaMemcpy(f->d_dft32, img.data(), img.size(), cudaMemcpyHostToDevice), "copy dft32");
+  }
   if (rc == TASR_OK && p->feature_type == TASR_FEAT_MFCC) {
     // tf.signal.mfccs_from_log_mel_spectrograms: dct(type 2, unnormalised: 2 sum x_n cos(pi k (2n+1)/(2M))) * rsqrt(2M)
     std::vector<float> dct((size_t)kMel * kMel);
@@ -139,6 +145,7 @@ extern "C" int tasr_featurizer_destroy(TasrFeaturizer* f) {
   cudaFree(f->d_band_w);
   cudaFree(f->d_bands);
   cudaFree(f->d_dct);
+  cudaFree(f->d_dft32);
   delete f;
   return TASR_OK;
 }

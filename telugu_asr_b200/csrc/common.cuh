@@ -85,11 +85,15 @@ struct TasrFeaturizer {
   float* d_dct;         // [80][80] mfcc basis D[n][k] = 2 cos(pi k (2n+1) / 160) / sqrt(160), or null
   int mel_fixed;        // 1: the matrix has the compiled-in config/model.yaml structure (mel_geometry.inc)
   float mel_fixed_w[512];  // wr[256] | wf[256], per FFT bin (kernel-parameter constants of the unrolled projection)
+  unsigned char* d_dft32;  // [16 KB] UMMA B images of the DFT-32 matrix, FP16 high | low parts (logmel_tc.cu)
 };
 
 // feature_post.cu: mfcc DCT and/or per-frame z-score / min-max normalisation, in place on [B, T_max, 80].
 int tasr_feature_post_launch(const TasrFeaturizer* f, float* feat, const int32_t* n_frames, int32_t B, int32_t T_max,
                              cudaStream_t st);
+
+// logmel_tc.cu: host builder of the DFT-32 operand images (16 KB)
+void tasr_logmel_tc_build_dft32(unsigned char* img16k);
 
 // logmel.cu: true (and wr_wf_512 filled) when the dense [257,80] matrix has the compiled-in structure.
 bool tasr_mel_fixed_from_dense(const float* mel_w_host, float* wr_wf_512);

@@ -463,6 +463,16 @@ static int logmel_launch(const TasrFeaturizer* f, const float* wav, const int32_
     a.floor_ = 0.0f;   // the floor is applied by the reader, after the gain (lg2(0) = -inf survives the addition)
     TASR_CUDA(cudaMemsetAsync(peak_out, 0, (size_t)B * sizeof(float), st));
   }
+  {
+    // default: second FFT stage on the tensor cores (logmel_tc.cu) when the handle has the compiled-in filterbank
+    const int rc_tc = tasr_logmel_tc_launch(f, a, st);
+    if (rc_tc >= 0) {
+      if (rc_tc != TASR_OK) return rc_tc;
+      if (f->p.feature_type == TASR_FEAT_MFCC || f->p.normalize_zscore || f->p.normalize_min_max)
+        return tasr_feature_post_launch(f, out, n_frames, B, T_max, st);
+      return TASR_OK;
+    }
+  }
   // Persistent grid: two CTAs per SM; never more CTAs than work items (valid tiles + padding chunks <= total + B).
   const long long cap = total + B;
   static const int ctas_per_sm = [] { const char* e = getenv("TASR_LOGMEL_CTAS_PER_SM"); const int v = e ? atoi(e) : 2; return v >= 1 && v <= 2 ? v : 2; }();

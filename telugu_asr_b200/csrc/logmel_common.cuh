@@ -101,3 +101,7 @@ __device__ __forceinline__ void mel_fixed_group(const float* Prow, const MelFixe
 
 
 }  // namespace tasr_lm
+
+// logmel_tc.cu: launches the tensor-core kernel; returns a negative value (and launches nothing) when the handle /
+// arguments are outside its scope, so that the caller falls back to logmel_kernel.
+int tasr_logmel_tc_launch(const TasrFeaturizer* f, const tasr_lm::LogmelArgs& a, cudaStream_t st);
