@@ -21,13 +21,23 @@
 // any input level; it is removed exactly after the mel projection.  tools/fft_tc_proto.py is the numpy model of these
 // numerics (8e-6 from the float64 oracle on the primary distribution, the same as the float32 oracle's own band).
 //
+// Work unit = a tile of 28 consecutive frames of one utterance: 9 x 28 = 252 GEMM rows = two M=128 UMMA tiles.
 // One persistent CTA per SM, 20 warps with roles (register budget re-dealt with setmaxnreg):
-//   warps 0-2    stagers: global -> shared samples of a 32-frame tile (gain, pre-emphasis in the reference's float32
-//                op order, tile max |x|, single-pass utterance peak), two tiles ahead, next tiles prefetched into L2;
-//   warp  3      MMA issuer: 36 tcgen05.mma (M=128, N=64, K=16, kind::f16) per tile into double-buffered TMEM;
-//   warps 4-11   producers: thread = (frame, four n1): window, FFT-16, twiddle, hi/lo split, swizzled UMMA A tiles;
+//   warp  0      loader: one cp.async.bulk (TMA bulk copy) per tile brings its raw samples (4 + 4720 floats, contiguous in
+//                the utterance) into a 4-deep shared ring, up to four tiles ahead; in single-pass mode the warp also takes
+//                max |x| of the few samples behind an utterance's last frame;
+//   warps 2-3    scanners: max |x| of a landed tile (-> the tile's power-of-two scale, and the utterance peak in
+//                single-pass mode), then hand the tile to the producers;
+//   warp  1      MMA issuer: per M-tile and K=16 slice  Ahi x [Bhi | Blo] (N=128)  and  Alo x Bhi (N=64, into the second
+//                half), i.e. the main product and the two correction products land in separate TMEM columns and are
+//                added in FP32 by the consumers; accumulators double-buffered (2 x 256 of the 512 columns);
+//   warps 4-11   producers: thread = (n1 pair, two consecutive frames): gain and pre-emphasis in the reference's float32
+//                op order (the sample before a pair comes from the neighbouring lane), tile scale, window,
+//                FFT-16, twiddle, hi/lo split, swizzled UMMA A rows; the pair's window and twiddles stay in registers;
 //   warps 12-19  consumers: TMEM -> |.|^2 -> P[frame][bin] -> banded mel projection (mel_geometry.inc) -> log ->
 //                coalesced stores; they also write the collate padding rows.
+// Hand-offs are mbarriers only: raw ring (TMA complete_tx / producer arrivals), the single A stage (producer arrivals /
+// tcgen05.commit), accumulators (tcgen05.commit / consumer arrivals).
 #include "logmel_common.cuh"
 #include "sepconv_common.cuh"
 #include <cuda_fp16.h>
@@ -43,45 +53,45 @@ using namespace tasr_sep;
 namespace {
 
 constexpr int kTcThreads = 640;
-constexpr int kStagerWarps = 3;
-constexpr int kStagerThreads = kStagerWarps * 32;
-constexpr int kWarpMmaTc = 3;
+constexpr int kWarpLoad = 0, kWarpMmaTc = 1;
 constexpr int kProdWarp0 = 4, kProdWarps = 8;
 constexpr int kConsWarp0 = 12, kConsWarps = 8;
 constexpr int kConsThreads = kConsWarps * 32;
 
-// A stage (one 32-frame tile): UMMA K-major SWIZZLE_128B blocks of 128-byte rows (64 FP16 = 32 n1 x (re, im)).
-//   [tile 2: p = 0, 32 rows: hi 4 KB | lo 4 KB][tile 0: p = 1..4, 128 rows: hi 16 KB | lo 16 KB][tile 1: p = 5..8: same]
-// The MMAs of tile 2 address 128 rows; rows 32..127 are whatever follows in the stage and only reach TMEM lanes nobody reads.
-constexpr int kStageBytes = 73728;
-constexpr int kOffT2Hi = 0, kOffT2Lo = 4096, kOffT0Hi = 8192, kOffT0Lo = 24576, kOffT1Hi = 40960, kOffT1Lo = 57344;
-// After a tile's MMAs have completed the consumers reuse its stage: P[32][261] power rows and the [32][81] output tile.
-constexpr int kPStrideTc = 261;
-constexpr int kOffP = 8192;
-constexpr int kOffOut = kOffP + kTileFrames * kPStrideTc * 4;          // 41600 (+10368 = 51968 <= kStageBytes)
-constexpr int kWavFloats = 5376;                                         // 31*160+400 = 5360, + 16 the last frame's n2 = 12 touches
-constexpr int kWavSlots4 = kWavFloats / 4;                               // 1344 = 14 * 96
+constexpr int kTcFrames = 28;                                            // frames per tile: 9 x 28 = 252 rows
+constexpr int kTcRows = 9 * kTcFrames;
+// A stage (one tile): UMMA K-major SWIZZLE_128B blocks of 128-byte rows (64 FP16 = 32 n1 x (re, im)); GEMM row
+// r = 28 p + f lives in M-tile r / 128:  [M-tile 0: hi 16 KB | lo 16 KB][M-tile 1: hi 16 KB | lo 16 KB].
+constexpr int kStageBytes = 65536;
+constexpr int kOffLo = 16384, kOffMt = 32768;
+constexpr int kPStrideTc = 261;                                          // P[32][261] power rows (28 used; lanes 28..31 of the mel phase
+constexpr int kPBytes = 32 * kPStrideTc * 4;                             //   work on the spare rows), [32][81] output tile
+constexpr int kOutBytes = 32 * kOutStride * 4;
+constexpr int kRawStages = 4;
+constexpr int kRawFloats = 4 + 4736;                                     // 4 samples before the tile, 27*160+400 = 4720 of it, 16 zeros
 constexpr int kListCapTc = 768;                                          // tiles per CTA per launch
 constexpr int kMaxUttTc = 1024;                                          // utterances per launch
-constexpr int kAccCols = 192;                                            // 3 M-tiles x 64 columns per accumulator buffer
+constexpr int kAccCols = 256;                                            // 2 M-tiles x (64 main + 64 correction) columns
 constexpr int kTmemColsTc = 512;
 
 struct TcLayout {
-  uint32_t a, wav, b, hwin, tw, vcum, pcum, list, lmax, bars, tmem_slot, total;
+  uint32_t a, raw, b, p, out, hwin, vcum, pcum, list, lmax, lgain, bars, tmem_slot, total;
 };
 __host__ __device__ inline TcLayout tc_layout() {
   TcLayout L;
   uint32_t o = 0;
-  L.a = o; o += 2 * kStageBytes;
+  L.a = o; o += kStageBytes;
   L.b = o; o += 16384;
-  L.wav = o; o += 2 * kWavFloats * 4;
+  L.raw = o; o += kRawStages * kRawFloats * 4;
+  L.p = o; o += kPBytes;
+  L.out = o; o += kOutBytes;
   L.hwin = o; o += 416 * 4;
-  L.tw = o; o += 512 * 4;
   L.vcum = o; o += (kMaxUttTc + 4) * 4;
   L.pcum = o; o += (kMaxUttTc + 4) * 4;
   L.list = o; o += kListCapTc * 8;
   L.lmax = o; o += kListCapTc * 4;
-  L.bars = o; o += 16 * 8;
+  L.lgain = o; o += kListCapTc * 4;
+  L.bars = o; o += 20 * 8;
   L.tmem_slot = o; o += 16;
   L.total = o;
   return L;
@@ -90,11 +100,27 @@ __host__ __device__ inline TcLayout tc_layout() {
 struct TcArgs {
   LogmelArgs a;
   const unsigned char* dft32;   // 16 KB: shared-memory images of the DFT-32 matrix, FP16 high part then low part
+  long long* trace;             // development aid (tools/tc_trace.py): per-role (tag, globaltimer) log of CTA 0, or null
+  int32_t ablate;               // development aid (TASR_TC_ABLATE): 1 no MMAs, 2 no stage-1 arithmetic, 4 no consumer arithmetic, 8 no sample loads
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ long long gtime_tc() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// role r logs (tag, time) pairs; 256 pairs per role
+#define TC_TRACE(role, tag)                                                                   \
+  do {                                                                                        \
+    if (ta.trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_n < 255) {               \
+      ta.trace[(role) * 512 + 2 * trace_n] = (tag);                                           \
+      ta.trace[(role) * 512 + 2 * trace_n + 1] = gtime_tc();                                  \
+      ++trace_n;                                                                              \
+    }                                                                                         \
+  } while (0)
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ uint32_t cvt_f16x2(float hi_half, float lo_half) {   // {upper 16 bits, lower 16 bits}
   uint32_t r;
@@ -112,6 +138,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 __device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory"); }
 
 // Power-of-two scale of a tile from its max |x| (bit pattern) and the utterance gain: with mg = max|x| * g in
@@ -134,31 +168,35 @@ __device__ __forceinline__ u64 hi11x2(u64 v) {
   return pack2(hi11(a), hi11(b));
 }
 // split of a packed complex pair (two n1) and its 8-byte stores into the A stage
-__device__ __forceinline__ void split_store(u64 re, u64 im, unsigned char* hi_ptr, unsigned char* lo_ptr) {
+__device__ __forceinline__ void split_store(u64 re, u64 im, unsigned char* hi_ptr) {
   const u64 re_h = hi11x2(re), im_h = hi11x2(im);
   const u64 re_l = sub2(re, re_h), im_l = sub2(im, im_h);
   float rha, rhb, iha, ihb, rla, rlb, ila, ilb;
   unpack2(re_h, rha, rhb); unpack2(im_h, iha, ihb);
   unpack2(re_l, rla, rlb); unpack2(im_l, ila, ilb);
   *reinterpret_cast<uint2*>(hi_ptr) = make_uint2(cvt_f16x2(iha, rha), cvt_f16x2(ihb, rhb));
-  *reinterpret_cast<uint2*>(lo_ptr) = make_uint2(cvt_f16x2(ila, rla), cvt_f16x2(ilb, rlb));
+  *reinterpret_cast<uint2*>(hi_ptr + kOffLo) = make_uint2(cvt_f16x2(ila, rla), cvt_f16x2(ilb, rlb));
 }
-__device__ __forceinline__ void split_store_real(u64 re, unsigned char* hi_ptr, unsigned char* lo_ptr) {
+__device__ __forceinline__ void split_store_real(u64 re, unsigned char* hi_ptr) {
   const u64 re_h = hi11x2(re);
   const u64 re_l = sub2(re, re_h);
   float rha, rhb, rla, rlb;
   unpack2(re_h, rha, rhb);
   unpack2(re_l, rla, rlb);
   *reinterpret_cast<uint2*>(hi_ptr) = make_uint2(cvt_f16x2(0.0f, rha), cvt_f16x2(0.0f, rhb));
-  *reinterpret_cast<uint2*>(lo_ptr) = make_uint2(cvt_f16x2(0.0f, rla), cvt_f16x2(0.0f, rlb));
+  *reinterpret_cast<uint2*>(hi_ptr + kOffLo) = make_uint2(cvt_f16x2(0.0f, rla), cvt_f16x2(0.0f, rlb));
+}
+// byte offset of GEMM row r, 16-byte chunk j8, 8-byte half pe inside the stage's hi blocks
+__device__ __forceinline__ int a_row_off(int r, int j8, int pe) {
+  return (r >> 7) * kOffMt + (r & 127) * 128 + ((j8 ^ (r & 7)) << 4) + pe * 8;
 }
 
-// Mel projection of one frame (lane) for the mel bins of group W, from the power row, with the tile scale removed
-// (acc * inv * inv, exact: inv is a power of two) before the floor and the log.  Same walk as tasr_lm::MelSeg.
+// Mel projection of one frame (lane) for the mel bins of group W from its power row: the same walk as tasr_lm::MelSeg
+// (every power bin feeds the rising side of bin m and the falling side of bin m-1, ascending k), but the sums stay in
+// registers until the whole group is done, so that the loads of the row are not fenced by the result stores.
 template <int M, int M0, int M1>
 struct MelSegTc {
-  static __device__ __forceinline__ void run(const float* __restrict__ Prow, const MelFixedW& w, float* __restrict__ srow,
-                                             float floor_, float scale, float inv, float acc_prev) {
+  static __device__ __forceinline__ void run(const float* __restrict__ Prow, const MelFixedW& w, float (&res)[M1 - M0], float acc_prev) {
     float acc_cur = 0.0f;
     constexpr int kBegin = kMelSegStart[M], kEnd = kMelSegStart[M + 1];
 #pragma unroll
@@ -167,61 +205,65 @@ struct MelSegTc {
       if (M < M1) acc_cur = fmaf(p, w.wr[k], acc_cur);
       if (M > M0) acc_prev = fmaf(p, w.wf[k], acc_prev);
     }
-    if (M > M0) srow[M - 1] = lg2_normal(fmaxf((acc_prev * inv) * inv, floor_)) * scale;
-    if constexpr (M < M1) MelSegTc<M + 1, M0, M1>::run(Prow, w, srow, floor_, scale, inv, acc_cur);
+    if constexpr (M > M0) res[M - 1 - M0] = acc_prev;
+    if constexpr (M < M1) MelSegTc<M + 1, M0, M1>::run(Prow, w, res, acc_cur);
   }
 };
+// tile scale removed (acc * inv * inv, exact: inv is a power of two) before the floor and the log
 template <int W>
 __device__ __forceinline__ void mel_group_tc(const float* Prow, const MelFixedW& w, float* srow, float floor_, float scale, float inv) {
-  MelSegTc<kMelGrp[W], kMelGrp[W], kMelGrp[W + 1]>::run(Prow, w, srow, floor_, scale, inv, 0.0f);
+  constexpr int M0 = kMelGrp[W], M1 = kMelGrp[W + 1];
+  float res[M1 - M0];
+  MelSegTc<M0, M0, M1>::run(Prow, w, res, 0.0f);
+#pragma unroll
+  for (int i = 0; i < M1 - M0; ++i) srow[M0 + i] = lg2_normal(fmaxf((res[i] * inv) * inv, floor_)) * scale;
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 logmel_tc_kernel(const __grid_constant__ TcArgs ta, const __grid_constant__ MelFixedW mw) {
   const LogmelArgs& a = ta.a;
   extern __shared__ unsigned char smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  unsigned char* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  const uint32_t raw_u = smem_u32(smem_raw);
+  unsigned char* sm = smem_raw + ((1024u - (raw_u & 1023u)) & 1023u);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const TcLayout L = tc_layout();
 
   unsigned char* sA = sm + L.a;
-  float* s_wav = reinterpret_cast<float*>(sm + L.wav);
+  float* s_raw = reinterpret_cast<float*>(sm + L.raw);
   float* s_hwin = reinterpret_cast<float*>(sm + L.hwin);
-  float* s_tw = reinterpret_cast<float*>(sm + L.tw);
   int32_t* vcum = reinterpret_cast<int32_t*>(sm + L.vcum);
   int32_t* pcum = reinterpret_cast<int32_t*>(sm + L.pcum);
   int2* list = reinterpret_cast<int2*>(sm + L.list);
   unsigned* lmax = reinterpret_cast<unsigned*>(sm + L.lmax);
+  float* lgain = reinterpret_cast<float*>(sm + L.lgain);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem_slot);
   const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sm + L.b), bar_u = smem_u32(sm + L.bars);
-  auto bar_wfull = [&](int s) { return bar_u + 8u * (uint32_t)s; };          // samples staged (one arrival per stager warp)
-  auto bar_wempty = [&](int s) { return bar_u + 8u * (uint32_t)(2 + s); };   // samples consumed (one per producer warp)
-  auto bar_afull = [&](int s) { return bar_u + 8u * (uint32_t)(4 + s); };    // A stage written (one per producer warp)
-  auto bar_aempty = [&](int s) { return bar_u + 8u * (uint32_t)(6 + s); };   // stage free again (one per consumer warp)
-  auto bar_accf = [&](int s) { return bar_u + 8u * (uint32_t)(8 + s); };     // accumulators complete (tcgen05.commit)
+  auto bar_wfull = [&](int s) { return bar_u + 8u * (uint32_t)s; };           // raw samples landed (TMA complete_tx)
+  auto bar_wempty = [&](int s) { return bar_u + 8u * (uint32_t)(4 + s); };    // raw samples consumed (one per producer warp)
+  const uint32_t bar_afull = bar_u + 8u * 8u;                                  // A stage written (one per producer warp)
+  const uint32_t bar_afree = bar_u + 8u * 9u;                                  // A stage read by the tensor core (tcgen05.commit)
+  auto bar_accf = [&](int s) { return bar_u + 8u * (uint32_t)(10 + s); };     // accumulators complete (tcgen05.commit)
+  auto bar_acce = [&](int s) { return bar_u + 8u * (uint32_t)(12 + s); };     // accumulators read (one per consumer warp)
+  auto bar_wready = [&](int s) { return bar_u + 8u * (uint32_t)(14 + s); };   // raw samples scanned for max |x| (one per scanner warp)
 
   // ---- prologue --------------------------------------------------------------------------------------------------
   for (int b = blockIdx.x * kTcThreads + tid; b < a.B; b += gridDim.x * kTcThreads) a.n_frames[b] = frames_of(a.len[b], a);
   if (warp == kWarpMmaTc) tmem_alloc(smem_u32(tmem_slot), kTmemColsTc);
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_wfull(s), kStagerWarps);
+    for (int s = 0; s < kRawStages; ++s) {
+      mbar_init(bar_wfull(s), 1);
+      mbar_init(bar_wready(s), 2);
       mbar_init(bar_wempty(s), kProdWarps);
-      mbar_init(bar_afull(s), kProdWarps);
-      mbar_init(bar_aempty(s), kConsWarps);
+    }
+    mbar_init(bar_afull, kProdWarps);
+    mbar_init(bar_afree, 1);
+    for (int s = 0; s < 2; ++s) {
       mbar_init(bar_accf(s), 1);
+      mbar_init(bar_acce(s), kConsWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < 416; i += kTcThreads) s_hwin[i] = a.hwin[i];
-  // twiddles W512^(n1 p) = (C, -S): table [j8][pe][p-1][C_a, C_b, S_a, S_b] for the n1 pair (4 j8 + 2 pe, +1)
-  for (int i = tid; i < 512; i += kTcThreads) {
-    const int c = i & 3, p = ((i >> 2) & 7) + 1, pe = (i >> 5) & 1, j8 = i >> 6;
-    const int n1 = 4 * j8 + 2 * pe + (c & 1);
-    const float2 w = a.tw512[n1 * p];
-    s_tw[i] = (c < 2) ? w.x : -w.y;
-  }
   {
     const uint4* src = reinterpret_cast<const uint4*>(ta.dft32);
     uint4* dst = reinterpret_cast<uint4*>(sm + L.b);
@@ -230,8 +272,8 @@ logmel_tc_kernel(const __grid_constant__ TcArgs ta, const __grid_constant__ MelF
   for (int i = tid; i < kListCapTc; i += kTcThreads) lmax[i] = 0u;
   for (int u = tid; u < a.B; u += kTcThreads) {
     const int Tu = frames_of(a.len[u], a);
-    const int vt = (Tu + kTileFrames - 1) / kTileFrames;
-    const int pad_rows = pad_limit(Tu, a) - vt * kTileFrames;
+    const int vt = (Tu + kTcFrames - 1) / kTcFrames;
+    const int pad_rows = pad_limit(Tu, a) - vt * kTcFrames;
     vcum[u + 1] = vt;
     pcum[u + 1] = pad_rows > 0 ? (pad_rows + kPadChunkRows - 1) / kPadChunkRows : 0;
   }
@@ -257,6 +299,7 @@ logmel_tc_kernel(const __grid_constant__ TcArgs ta, const __grid_constant__ MelF
   const int G = (int)gridDim.x, me = (int)blockIdx.x;
   const int n_v = (total_v > me) ? (total_v - me - 1) / G + 1 : 0;   // <= kListCapTc (checked by the host)
   const int n_p = (total_p > me) ? (total_p - me - 1) / G + 1 : 0;
+  const bool single_pass = (a.peak_out != nullptr);
   auto find = [&](const int32_t* cum, int x) -> int {   // largest u in [0,B) with cum[u] <= x
     int lo = 0, hi = a.B;
     while (hi - lo > 1) {
@@ -269,226 +312,246 @@ logmel_tc_kernel(const __grid_constant__ TcArgs ta, const __grid_constant__ MelF
     const int j = me + k * G;
     const int u = find(vcum, j);
     list[k] = make_int2((u << 16) | (j - vcum[u]), a.len[u]);
+    // the utterance gain rides in the list (no global load in the tile loops); src/speech_featurizer.py:70
+    lgain[k] = (a.normalize && !single_pass) ? __fdiv_rn(1.0f, __fadd_rn(a.peak[u], 1e-9f)) : 1.0f;
   }
   fence_async_smem();     // the DFT-32 images were written through the generic proxy; the tensor core reads them
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const bool single_pass = (a.peak_out != nullptr);
+  int trace_n = 0;
+  if (ta.trace != nullptr && blockIdx.x == 0 && tid == 0) { ta.trace[5 * 512] = n_v; ta.trace[5 * 512 + 1] = gtime_tc(); }
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (warp < kStagerWarps) {
-      // =========================== stagers =====================================================================
-      const float c = a.preemph;
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == kWarpLoad) {
+      // =========================== loader (TMA bulk copies) ===================================================
+      // raw stage: [0,4) the four samples before the tile (zeros at the start of an utterance: y[0] = x[0] - c*0),
+      // [4, 4+count) the tile, then 16 zeros (the last frame's zero-weight window tail must read finite values).
       for (int k = 0; k < n_v; ++k) {
-        const int s = k & 1;
+        const int sw = k % kRawStages;
         const int2 item = list[k];
         const int u = item.x >> 16, tf = item.x & 0xffff, n = item.y;
         const int Tb = frames_of(n, a);
-        const int f0 = tf * kTileFrames;
-        const int nvalid = min(kTileFrames, Tb - f0);
+        const int f0 = tf * kTcFrames;
+        const int nvalid = min(kTcFrames, Tb - f0);
         const int s0 = f0 * kFrameStep;
         const int count = (nvalid - 1) * kFrameStep + kFrameLen;       // multiple of 4; s0 + count <= n
         const float* row = a.wav + (size_t)u * a.row_stride;
-        if (k + 2 < n_v) {                                               // the tile after next -> L2 (168 lines of 128 B)
-          const int2 nx = list[k + 2];
-          const float* nrow = a.wav + (size_t)(nx.x >> 16) * a.row_stride;
-          const int nb = (nx.x & 0xffff) * kTileFrames * kFrameStep;
-          for (int l = tid; l < 168; l += kStagerThreads)
-            if (nb + l * 32 < nx.y) prefetch_l2(nrow + nb + l * 32);
-        }
-        float g = 1.0f;
-        if (a.normalize && !single_pass) g = __fdiv_rn(1.0f, __fadd_rn(a.peak[u], 1e-9f));   // src/speech_featurizer.py:70
-        if (k >= 2) mbar_wait(bar_wempty(s), ((k >> 1) - 1) & 1);
-        float* wv = s_wav + s * kWavFloats;
-        unsigned m = 0u;
-#pragma unroll 1
-        for (int batch = 0; batch < 2; ++batch) {
-          float4 x[7];
-          float xp[7];
-#pragma unroll
-          for (int q = 0; q < 7; ++q) {
-            const int i4 = tid + (batch * 7 + q) * kStagerThreads;
-            x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            xp[q] = 0.0f;
-            if (4 * i4 < count) {
-              x[q] = *reinterpret_cast<const float4*>(row + s0 + 4 * i4);
-              if (s0 + 4 * i4 > 0) xp[q] = row[s0 + 4 * i4 - 1];
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 7; ++q) {
-            const int i4 = tid + (batch * 7 + q) * kStagerThreads;
-            m = max(max(m, max(abs_bits(x[q].x), abs_bits(x[q].y))), max(abs_bits(x[q].z), abs_bits(x[q].w)));
-            if (4 * i4 < count + 16) {                                   // [count, count+16) must be finite zeros (window tail)
-              float4 v = x[q];
-              v.x = __fmul_rn(v.x, g); v.y = __fmul_rn(v.y, g); v.z = __fmul_rn(v.z, g); v.w = __fmul_rn(v.w, g);   // :71
-              float4 y = v;
-              if (c > 0.0f) {   // :75-79  y[0]=x[0]; y[n]=x[n]-c*x[n-1], product and difference rounded separately
-                const float vp = __fmul_rn(xp[q], g);
-                y.x = (s0 + 4 * i4 > 0) ? __fsub_rn(v.x, __fmul_rn(c, vp)) : v.x;
-                y.y = __fsub_rn(v.y, __fmul_rn(c, v.x));
-                y.z = __fsub_rn(v.z, __fmul_rn(c, v.y));
-                y.w = __fsub_rn(v.w, __fmul_rn(c, v.z));
-              }
-              *reinterpret_cast<float4*>(wv + 4 * i4) = y;
-            }
-          }
-        }
-        const unsigned mt = __reduce_max_sync(0xffffffffu, m);
-        if (lane == 0 && mt != 0u) atomicMax(&lmax[k], mt);
-        if (single_pass) {
-          // the tile holding the utterance's last frame also takes the samples no frame covers, [s0+count, n)
-          if (f0 + nvalid >= Tb) {
-            for (int i = s0 + count + 4 * tid; i < n; i += 4 * kStagerThreads) {
-              const float4 t4 = *reinterpret_cast<const float4*>(row + i);
-              m = max(m, abs_bits(t4.x));
-              if (i + 1 < n) m = max(m, abs_bits(t4.y));
-              if (i + 2 < n) m = max(m, abs_bits(t4.z));
-              if (i + 3 < n) m = max(m, abs_bits(t4.w));
-            }
-          }
-          const unsigned mb = __reduce_max_sync(0xffffffffu, m);
-          if (lane == 0 && mb != 0u) atomicMax(reinterpret_cast<unsigned*>(a.peak_out) + u, mb);
-        }
+        if (k >= kRawStages) mbar_wait(bar_wempty(sw), ((k / kRawStages) - 1) & 1);
+        TC_TRACE(0, 1000 + k);
+        float* rw = s_raw + sw * kRawFloats;
+        if (lane < 4) *reinterpret_cast<float4*>(rw + 4 + count + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane == 4 && s0 == 0) *reinterpret_cast<float4*>(rw) = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_wfull(s));
+        if (lane == 0) {
+          const int pre = (s0 > 0) ? 4 : 0;
+          const uint32_t bytes = (ta.ablate & 8) ? 16u : (uint32_t)(count + pre) * 4u;
+          mbar_expect_tx(bar_wfull(sw), bytes);
+          bulk_g2s(smem_u32(rw + 4 - pre), row + s0 - pre, bytes, bar_wfull(sw));
+        }
+        if (single_pass && f0 + nvalid >= Tb) {
+          // the utterance's last tile: max |x| of the samples no frame covers, [s0+count, n) (fewer than 160)
+          unsigned m = 0u;
+          for (int i = s0 + count + lane; i < n; i += 32) m = max(m, abs_bits(row[i]));
+          m = __reduce_max_sync(0xffffffffu, m);
+          if (lane == 0 && m != 0u) atomicMax(reinterpret_cast<unsigned*>(a.peak_out) + u, m);
+        }
       }
-    } else if (lane == 0) {
-      // =========================== MMA issuer ==================================================================
-      const uint32_t idesc = umma_idesc_f16(128, 64);
-      const uint64_t db_hi = umma_desc_sw128(sB_u), db_lo = umma_desc_sw128(sB_u + 8192u);
+    } else if (warp >= 2) {
+      // =========================== scanners ====================================================================
+      const int sc = warp - 2;                       // each scanner takes every other float4 of the tile
       for (int k = 0; k < n_v; ++k) {
-        const int s = k & 1;
-        mbar_wait(bar_afull(s), (k >> 1) & 1);
+        const int sw = k % kRawStages;
+        const int2 item = list[k];
+        const int u = item.x >> 16, tf = item.x & 0xffff;
+        const int nvalid = min(kTcFrames, frames_of(item.y, a) - tf * kTcFrames);
+        const int count4 = ((nvalid - 1) * kFrameStep + kFrameLen) >> 2;
+        mbar_wait(bar_wfull(sw), (k / kRawStages) & 1);
+        const float4* rw4 = reinterpret_cast<const float4*>(s_raw + sw * kRawFloats + 4);
+        unsigned m = 0u;
+        if (!(ta.ablate & 8))
+          for (int i = 2 * lane + sc; i < count4; i += 64) {
+            const float4 x = rw4[i];
+            m = max(max(m, max(abs_bits(x.x), abs_bits(x.y))), max(abs_bits(x.z), abs_bits(x.w)));
+          }
+        m = __reduce_max_sync(0xffffffffu, m);
+        if (lane == 0) {
+          if (m != 0u) {
+            atomicMax(&lmax[k], m);
+            if (single_pass) atomicMax(reinterpret_cast<unsigned*>(a.peak_out) + u, m);
+          }
+          mbar_arrive(bar_wready(sw));
+        }
+      }
+    } else if (warp == kWarpMmaTc && lane == 0) {
+      // =========================== MMA issuer ==================================================================
+      const uint32_t idesc128 = umma_idesc_f16(128, 128), idesc64 = umma_idesc_f16(128, 64);
+      const uint64_t db = umma_desc_sw128(sB_u);      // rows 0..63 = Bhi, rows 64..127 = Blo (the two images are contiguous)
+      for (int k = 0; k < n_v; ++k) {
+        const int acc = k & 1;
+        mbar_wait(bar_afull, k & 1);
+        if (k >= 2) mbar_wait(bar_acce(acc), ((k >> 1) - 1) & 1);
         tc_fence_after();
-        const uint32_t base = sA_u + (uint32_t)s * kStageBytes;
+        TC_TRACE(1, 1000 + k);
 #pragma unroll
-        for (int mt = 0; mt < 3; ++mt) {
-          const uint32_t hi_off = (mt == 0) ? kOffT0Hi : (mt == 1) ? kOffT1Hi : kOffT2Hi;
-          const uint32_t lo_off = (mt == 0) ? kOffT0Lo : (mt == 1) ? kOffT1Lo : kOffT2Lo;
-          const uint64_t da_hi = umma_desc_sw128(base + hi_off), da_lo = umma_desc_sw128(base + lo_off);
-          const uint32_t d = tmem + (uint32_t)(s * kAccCols + mt * 64);
+        for (int mt = 0; mt < 2; ++mt) {
+          if (ta.ablate & 1) break;
+          const uint64_t da_hi = umma_desc_sw128(sA_u + mt * kOffMt), da_lo = umma_desc_sw128(sA_u + mt * kOffMt + kOffLo);
+          const uint32_t d = tmem + (uint32_t)(acc * kAccCols + mt * 128);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            umma_f16(d, da_hi + (uint64_t)(2 * j), db_hi + (uint64_t)(2 * j), idesc, j != 0 ? 1u : 0u);
-            umma_f16(d, da_lo + (uint64_t)(2 * j), db_hi + (uint64_t)(2 * j), idesc, 1u);
-            umma_f16(d, da_hi + (uint64_t)(2 * j), db_lo + (uint64_t)(2 * j), idesc, 1u);
+            umma_f16(d, da_hi + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc128, j != 0 ? 1u : 0u);   // [Ahi Bhi | Ahi Blo]
+            umma_f16(d + 64u, da_lo + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc64, 1u);             // + Alo Bhi
           }
         }
-        umma_commit(bar_accf(s));
+        umma_commit(bar_afree);
+        umma_commit(bar_accf(acc));
+        TC_TRACE(1, 2000 + k);
       }
     }
   } else if (warp < kConsWarp0) {
     // =========================== producers =======================================================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    // thread = (n1 pair c, frame slot): lanes 0-15 / 16-31 of a warp are the sixteen n1 pairs (4 j8 + 2 pe, +1) of two
+    // frame slots; a slot is two consecutive frames, whose sample windows overlap by 8 of 13 polyphase values.  The
+    // pair's window and twiddles live in registers for the whole kernel: no table loads in the loop.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
     const int ptid = tid - kProdWarp0 * 32;
-    const int f = ptid >> 3, j8 = ptid & 7;
+    const int c16 = lane & 15, j8 = c16 >> 1, pe = c16 & 1;
+    const int fa = 2 * ((ptid >> 5) * 2 + (lane >> 4));        // first frame of this thread's slot (0, 2, .., 30; 28 and 30 idle)
     constexpr float kH = 0.70710678118654752440f, kC1 = 0.92387953251128675613f, kS1 = 0.38268343236508977173f;
     const u64 H2 = pack2(kH, kH), NH2 = pack2(-kH, -kH), C12 = pack2(kC1, kC1), S12 = pack2(kS1, kS1), Z2 = pack2(0.f, 0.f);
+    const float cpre = a.preemph;
+    const u64 CP2 = pack2(cpre, cpre);
+    u64 wreg[13], twc[8], tws[8];
+#pragma unroll
+    for (int n2 = 0; n2 < 13; ++n2) wreg[n2] = *reinterpret_cast<const u64*>(s_hwin + 4 * j8 + 2 * pe + 32 * n2);
+#pragma unroll
+    for (int p = 1; p <= 8; ++p) {      // W512^(n1 p) = C - i S for the pair's two n1
+      const int n1 = 4 * j8 + 2 * pe;
+      const float2 w0 = a.tw512[n1 * p], w1 = a.tw512[(n1 + 1) * p];
+      twc[p - 1] = pack2(w0.x, w1.x);
+      tws[p - 1] = pack2(-w0.y, -w1.y);
+    }
     for (int k = 0; k < n_v; ++k) {
-      const int s = k & 1;
+      const int sw = k % kRawStages;
       const int2 item = list[k];
-      const int u = item.x >> 16, tf = item.x & 0xffff;
-      const int nvalid = min(kTileFrames, frames_of(item.y, a) - tf * kTileFrames);
-      mbar_wait(bar_wfull(s), (k >> 1) & 1);
-      float g = 1.0f;
-      if (a.normalize && !single_pass) g = __fdiv_rn(1.0f, __fadd_rn(a.peak[u], 1e-9f));
+      const int tf = item.x & 0xffff;
+      const int nvalid = min(kTcFrames, frames_of(item.y, a) - tf * kTcFrames);
+      const float g = lgain[k];
+      const u64 G2 = pack2(g, g);
+      mbar_wait(bar_wready(sw), (k / kRawStages) & 1);
+      if (warp == kProdWarp0) TC_TRACE(2, 1000 + k);
+      const bool act_a = (fa < nvalid) && !(ta.ablate & 2), act_b = (fa + 1 < nvalid) && !(ta.ablate & 2);
       float s2f, invf;
       tile_scales(lmax[k], g, s2f, invf);
       const u64 S2 = pack2(s2f, s2f);
-      if (k >= 2) mbar_wait(bar_aempty(s), ((k >> 1) - 1) & 1);
-      if (f < nvalid) {
-        unsigned char* stage = sA + s * kStageBytes;
+      bool waited = false;
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          const int pe = pass ^ (f & 1);     // odd frames take the n1 pairs in the other order: conflict-free 8-byte accesses
-          const float* yp = s_wav + s * kWavFloats + f * kFrameStep + 4 * j8 + 2 * pe;
-          const float* wp = s_hwin + 4 * j8 + 2 * pe;
-          u64 uu[13];
+      for (int fi = 0; fi < 2; ++fi) {
+        const int f = fa + fi;
+        const bool active = (fi == 0) ? act_a : act_b;       // (the shuffles below need the whole warp: idle lanes compute along)
+        if (!__any_sync(0xffffffffu, active)) break;
+        // ---- raw samples of this n1 pair -> gain, pre-emphasis (src/speech_featurizer.py:70-79), tile scale, window -----
+        u64 uu[13];
+        {
+          const float* xp = s_raw + sw * kRawFloats + 4 + f * kFrameStep + 4 * j8 + 2 * pe;
+          const float x_before = xp[-1];             // the sample before the pair's first one (used by pair 0 at n2 = 0)
+          float v15_prev = 0.0f;                      // pair 15's gained second sample of the previous n2
 #pragma unroll
           for (int n2 = 0; n2 < 13; ++n2) {
-            const u64 y = *reinterpret_cast<const u64*>(yp + 32 * n2);
-            const u64 w = *reinterpret_cast<const u64*>(wp + 32 * n2);
-            uu[n2] = mul2(mul2(y, S2), w);
-          }
-          // ---- real-input FFT-16 of (u0..u12, 0, 0, 0): X0, X8 real, X1..X7 complex -------------------------
-          const u64 e0 = add2(uu[0], uu[8]), e1 = add2(uu[1], uu[9]), e2 = add2(uu[2], uu[10]), e3 = add2(uu[3], uu[11]),
-                    e4 = add2(uu[4], uu[12]), e5 = uu[5], e6 = uu[6], e7 = uu[7];
-          const u64 o0 = sub2(uu[0], uu[8]), o1 = sub2(uu[1], uu[9]), o2 = sub2(uu[2], uu[10]), o3 = sub2(uu[3], uu[11]),
-                    o4 = sub2(uu[4], uu[12]), o4n = sub2(uu[12], uu[4]), o5 = uu[5], o5n = sub2(Z2, uu[5]), o6 = uu[6], o7 = uu[7];
-          u64 xr[9], xi[9];
-          {
-            const u64 ee0 = add2(e0, e4), ee1 = add2(e1, e5), ee2 = add2(e2, e6), ee3 = add2(e3, e7);
-            const u64 eo0 = sub2(e0, e4), eo1 = sub2(e1, e5), eo2 = sub2(e2, e6), eo2n = sub2(e6, e2), eo3 = sub2(e3, e7);
-            const u64 aa = add2(ee0, ee2), bb = add2(ee1, ee3);
-            xr[0] = add2(aa, bb);
-            xr[8] = sub2(aa, bb);
-            xr[4] = sub2(ee0, ee2);
-            xi[4] = sub2(ee3, ee1);
-            const u64 sd = sub2(eo1, eo3), sm_ = add2(eo1, eo3);
-            xr[2] = fma2(sd, H2, eo0);
-            xr[6] = fma2(sd, NH2, eo0);
-            xi[2] = fma2(sm_, NH2, eo2n);
-            xi[6] = fma2(sm_, NH2, eo2);
-          }
-          {
-            u64 sd = sub2(o2, o6), sm_ = add2(o2, o6);
-            const u64 A0r = fma2(sd, H2, o0), A1r = fma2(sd, NH2, o0), A0i = fma2(sm_, NH2, o4n), A1i = fma2(sm_, NH2, o4);
-            sd = sub2(o3, o7); sm_ = add2(o3, o7);
-            const u64 B0r = fma2(sd, H2, o1), B1r = fma2(sd, NH2, o1), B0i = fma2(sm_, NH2, o5n), B1i = fma2(sm_, NH2, o5);
-            const u64 P1 = fma2(S12, B0i, mul2(C12, B0r)), Q1 = sub2(mul2(C12, B0i), mul2(S12, B0r));
-            const u64 P3 = fma2(C12, B1i, mul2(S12, B1r)), Q3 = sub2(mul2(S12, B1i), mul2(C12, B1r));
-            xr[1] = add2(A0r, P1); xi[1] = add2(A0i, Q1);
-            xr[7] = sub2(A0r, P1); xi[7] = sub2(Q1, A0i);
-            xr[3] = add2(A1r, P3); xi[3] = add2(A1i, Q3);
-            xr[5] = sub2(A1r, P3); xi[5] = sub2(Q3, A1i);
-          }
-          // ---- twiddle, split, store ----------------------------------------------------------------------
-          const int row7 = f & 7;
-          unsigned char* rowp = stage + f * 128 + ((j8 ^ row7) << 4) + pe * 8;
-          split_store_real(xr[0], rowp + kOffT2Hi, rowp + kOffT2Lo);
-          const float4* tq = reinterpret_cast<const float4*>(s_tw) + (j8 * 2 + pe) * 8;
-#pragma unroll
-          for (int p = 1; p <= 8; ++p) {
-            const float4 t4 = tq[p - 1];
-            const u64 C = pack2(t4.x, t4.y), S = pack2(t4.z, t4.w);   // W512^(n1 p) = C - i S
-            u64 vr, vi;
-            if (p < 8) {
-              vr = fma2(xi[p], S, mul2(xr[p], C));
-              vi = sub2(mul2(xi[p], C), mul2(xr[p], S));
-            } else {
-              vr = mul2(xr[8], C);
-              vi = sub2(Z2, mul2(xr[8], S));
-            }
-            const int blk = (p <= 4) ? (kOffT0Hi + (p - 1) * 4096) : (kOffT1Hi + (p - 5) * 4096);
-            split_store(vr, vi, rowp + blk, rowp + blk + 16384);
+            const u64 v2 = mul2(*reinterpret_cast<const u64*>(xp + 32 * n2), G2);             // :71  x * gain
+            float va, vb;
+            unpack2(v2, va, vb);
+            // the gained sample before va: the neighbouring pair's second sample; pair 0 takes pair 15's of the previous n2
+            float vp = __shfl_up_sync(0xffffffffu, vb, 1, 16);
+            const float v15 = __shfl_sync(0xffffffffu, vb, 15, 16);
+            if (c16 == 0) vp = (n2 == 0) ? __fmul_rn(x_before, g) : v15_prev;
+            v15_prev = v15;
+            const u64 y2 = (cpre > 0.0f) ? sub2(v2, mul2(CP2, pack2(vp, va))) : v2;          // :77-79  y[n] = x[n] - c x[n-1]
+            uu[n2] = mul2(mul2(y2, S2), wreg[n2]);
           }
         }
+        // ---- real-input FFT-16 of (u0..u12, 0, 0, 0): X0, X8 real, X1..X7 complex -------------------------
+        const u64 e0 = add2(uu[0], uu[8]), e1 = add2(uu[1], uu[9]), e2 = add2(uu[2], uu[10]), e3 = add2(uu[3], uu[11]),
+                  e4 = add2(uu[4], uu[12]), e5 = uu[5], e6 = uu[6], e7 = uu[7];
+        const u64 o0 = sub2(uu[0], uu[8]), o1 = sub2(uu[1], uu[9]), o2 = sub2(uu[2], uu[10]), o3 = sub2(uu[3], uu[11]),
+                  o4 = sub2(uu[4], uu[12]), o4n = sub2(uu[12], uu[4]), o5 = uu[5], o5n = sub2(Z2, uu[5]), o6 = uu[6], o7 = uu[7];
+        u64 xr[9], xi[9];
+        {
+          const u64 ee0 = add2(e0, e4), ee1 = add2(e1, e5), ee2 = add2(e2, e6), ee3 = add2(e3, e7);
+          const u64 eo0 = sub2(e0, e4), eo1 = sub2(e1, e5), eo2 = sub2(e2, e6), eo2n = sub2(e6, e2), eo3 = sub2(e3, e7);
+          const u64 aa = add2(ee0, ee2), bb = add2(ee1, ee3);
+          xr[0] = add2(aa, bb);
+          xr[8] = sub2(aa, bb);
+          xr[4] = sub2(ee0, ee2);
+          xi[4] = sub2(ee3, ee1);
+          const u64 sd = sub2(eo1, eo3), sm_ = add2(eo1, eo3);
+          xr[2] = fma2(sd, H2, eo0);
+          xr[6] = fma2(sd, NH2, eo0);
+          xi[2] = fma2(sm_, NH2, eo2n);
+          xi[6] = fma2(sm_, NH2, eo2);
+        }
+        {
+          u64 sd = sub2(o2, o6), sm_ = add2(o2, o6);
+          const u64 A0r = fma2(sd, H2, o0), A1r = fma2(sd, NH2, o0), A0i = fma2(sm_, NH2, o4n), A1i = fma2(sm_, NH2, o4);
+          sd = sub2(o3, o7); sm_ = add2(o3, o7);
+          const u64 B0r = fma2(sd, H2, o1), B1r = fma2(sd, NH2, o1), B0i = fma2(sm_, NH2, o5n), B1i = fma2(sm_, NH2, o5);
+          const u64 P1 = fma2(S12, B0i, mul2(C12, B0r)), Q1 = sub2(mul2(C12, B0i), mul2(S12, B0r));
+          const u64 P3 = fma2(C12, B1i, mul2(S12, B1r)), Q3 = sub2(mul2(S12, B1i), mul2(C12, B1r));
+          xr[1] = add2(A0r, P1); xi[1] = add2(A0i, Q1);
+          xr[7] = sub2(A0r, P1); xi[7] = sub2(Q1, A0i);
+          xr[3] = add2(A1r, P3); xi[3] = add2(A1i, Q3);
+          xr[5] = sub2(A1r, P3); xi[5] = sub2(Q3, A1i);
+        }
+        // the single A stage is free again once the previous tile's MMAs have read it
+        if (fi == 0 && k >= 1) { mbar_wait(bar_afree, (k - 1) & 1); waited = true; }
+        // ---- twiddle, split, store: GEMM row 28 p + f ---------------------------------------------------
+        if (!active) continue;
+        split_store_real(xr[0], sA + a_row_off(f, j8, pe));
+#pragma unroll
+        for (int p = 1; p <= 8; ++p) {
+          const u64 C = twc[p - 1], S = tws[p - 1];
+          u64 vr, vi;
+          if (p < 8) {
+            vr = fma2(xi[p], S, mul2(xr[p], C));
+            vi = sub2(mul2(xi[p], C), mul2(xr[p], S));
+          } else {
+            vr = mul2(xr[8], C);
+            vi = sub2(Z2, mul2(xr[8], S));
+          }
+          split_store(vr, vi, sA + a_row_off(kTcFrames * p + f, j8, pe));
+        }
       }
+      // A warp with no active frame stores nothing, but it must not run ahead either: mbarrier arrivals are not tagged
+      // with a phase, so its arrival for this tile may only be made once the previous tile's phase has completed.
+      if (!waited && k >= 1) mbar_wait(bar_afree, (k - 1) & 1);
       fence_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar_afull(s));
-        mbar_arrive(bar_wempty(s));
+        mbar_arrive(bar_afull);
+        mbar_arrive(bar_wempty(sw));
       }
+      if (warp == kProdWarp0) TC_TRACE(2, 3000 + k);
     }
   } else {
     // =========================== consumers =======================================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     const int e = warp - kConsWarp0;
-    const int q = e & 3, half = e >> 2;          // TMEM lane quadrant (= warp id % 4), M-tile
-    const int p = 1 + q + 4 * half;
+    const int q = e & 3, mt = e >> 2;            // TMEM lane quadrant (= warp id % 4), M-tile
+    const int grow = mt * 128 + q * 32 + lane;   // this thread's GEMM row = 28 p + f
+    const int p = grow / kTcFrames, fr = grow - p * kTcFrames;
     const int ctid = tid - kConsWarp0 * 32;
+    float* P = reinterpret_cast<float*>(sm + L.p);
+    float* ostg = reinterpret_cast<float*>(sm + L.out);
     int pdone = 0;
     auto do_fill = [&](int upto) {               // collate padding: rows beyond the last valid tile, 128-row chunks
       for (; pdone < upto; ++pdone) {
         const int j = me + pdone * G;
         const int u = find(pcum, j);
         const int vt = vcum[u + 1] - vcum[u];
-        const int r0 = vt * kTileFrames + (j - pcum[u]) * kPadChunkRows;
+        const int r0 = vt * kTcFrames + (j - pcum[u]) * kPadChunkRows;
         const int rows = min(kPadChunkRows, pad_limit(frames_of(a.len[u], a), a) - r0);
         float* dst = a.out + ((size_t)u * a.T_max + r0) * kMel;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -496,53 +559,52 @@ logmel_tc_kernel(const __grid_constant__ TcArgs ta, const __grid_constant__ MelF
       }
     };
     for (int k = 0; k < n_v; ++k) {
-      const int s = k & 1;
+      const int acc = k & 1;
       const int2 item = list[k];
       const int u = item.x >> 16, tf = item.x & 0xffff;
       const int Tb = frames_of(item.y, a);
-      const int f0 = tf * kTileFrames;
-      const int nvalid = min(kTileFrames, Tb - f0);
-      const int rows = min(kTileFrames, a.T_max - f0);
-      float g = 1.0f;
-      if (a.normalize && !single_pass) g = __fdiv_rn(1.0f, __fadd_rn(a.peak[u], 1e-9f));
+      const int f0 = tf * kTcFrames;
+      const int nvalid = min(kTcFrames, Tb - f0);
+      const int rows = min(kTcFrames, a.T_max - f0);
+      const float g = lgain[k];
       // a NaN peak (a NaN sample somewhere in the utterance) makes every feature of the utterance NaN, as in the reference
       const float floor_b = (g != g) ? g : a.floor_;
-      float* P = reinterpret_cast<float*>(sA + s * kStageBytes + kOffP);
-      float* ostg = reinterpret_cast<float*>(sA + s * kStageBytes + kOffOut);
-      mbar_wait(bar_accf(s), (k >> 1) & 1);
+      mbar_wait(bar_accf(acc), (k >> 1) & 1);
       tc_fence_after();
+      if (e == 0) TC_TRACE(3, 1000 + k);
       float s2f, invf;
       tile_scales(lmax[k], g, s2f, invf);
-      float* Prow = P + lane * kPStrideTc;
-      {
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols + half * 64);
-        uint32_t r[32];
-        tmem_ld32(taddr, r);
+      if (!(ta.ablate & 4)) {
+        // F_p[k1'] = main + correction columns; X[16 k1' + p] (k1' < 16) and conj X[256 - 16 (k1' - 16) - p] (k1' >= 16, 0 < p < 8)
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + mt * 128);
+        float* Pw = P + fr * kPStrideTc;
+        const bool row_ok = (grow < kTcRows);
+        const bool second = row_ok && p >= 1 && p <= 7;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float re = __uint_as_float(r[2 * i]), im = __uint_as_float(r[2 * i + 1]);
-          Prow[16 * i + p] = fmaf(re, re, im * im);                       // X[16 k1' + p]
-        }
-        if (p < 8) {
-          tmem_ld32(taddr + 32u, r);
+        for (int cc = 0; cc < 4; ++cc) {
+          if (cc >= 2 && !__any_sync(0xffffffffu, second)) break;
+          uint32_t rm[16], rc[16];
+          tmem_ld16_nowait(taddr + 16u * cc, rm);
+          tmem_ld16_nowait(taddr + 64u + 16u * cc, rc);
+          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float re = __uint_as_float(r[2 * i]), im = __uint_as_float(r[2 * i + 1]);
-            Prow[256 - 16 * i - p] = fmaf(re, re, im * im);               // conj X[512 - 16 (16 + i) - p]
-          }
-        }
-        if (e == 0) {                                                      // p = 0 rows live in M-tile 2, lanes 0..31
-          tmem_ld32(tmem + (uint32_t)(s * kAccCols + 128), r);
-#pragma unroll
-          for (int i = 1; i < 16; ++i) {
-            const float re = __uint_as_float(r[2 * i]), im = __uint_as_float(r[2 * i + 1]);
-            Prow[16 * i] = fmaf(re, re, im * im);
+          for (int i = 0; i < 8; ++i) {
+            const float re = __uint_as_float(rm[2 * i]) + __uint_as_float(rc[2 * i]);
+            const float im = __uint_as_float(rm[2 * i + 1]) + __uint_as_float(rc[2 * i + 1]);
+            const float pw = fmaf(re, re, im * im);
+            const int k1 = 8 * cc + i;
+            if (cc < 2) { if (row_ok) Pw[16 * k1 + p] = pw; }
+            else if (second) Pw[256 - 16 * (k1 - 16) - p] = pw;
           }
         }
       }
       tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce(acc));     // this warp has read its part of the accumulators
       cons_bar();
-      {
+      if (e == 0) TC_TRACE(3, 2000 + k);
+      if (!(ta.ablate & 4)) {
+        const float* Prow = P + lane * kPStrideTc;     // lane = frame (lanes 28..31 work on the spare rows)
         float* srow = ostg + lane * kOutStride;
         switch (e) {
           case 0: mel_group_tc<0>(Prow, mw, srow, floor_b, a.log_scale, invf); break;
@@ -556,7 +618,8 @@ logmel_tc_kernel(const __grid_constant__ TcArgs ta, const __grid_constant__ MelF
         }
       }
       cons_bar();
-      {
+      if (e == 0) TC_TRACE(3, 3000 + k);
+      if (!(ta.ablate & 4)) {
         // coalesced store; rows beyond n_frames[b] inside this tile are the collate's 0.0
         float* orow = a.out + ((size_t)u * a.T_max + f0) * kMel;
         for (int i = ctid; i < rows * (kMel / 4); i += kConsThreads) {
@@ -569,11 +632,11 @@ logmel_tc_kernel(const __grid_constant__ TcArgs ta, const __grid_constant__ MelF
           st_global_v4(orow + 4 * i, o);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_aempty(s));
+      if (e == 0) TC_TRACE(3, 4000 + k);
       do_fill((int)(((long long)n_p * (k + 1)) / n_v));
     }
     do_fill(n_p);
+    if (e == 0) TC_TRACE(3, 9000);
   }
   tc_fence_before();
   __syncthreads();
@@ -621,6 +684,10 @@ void tasr_logmel_tc_build_dft32(unsigned char* img16k) {
   }
 }
 
+static long long* g_tc_trace = nullptr;
+// Development aid: a device buffer of 6*512 int64 that CTA 0 of the next launches logs (tag, ns) pairs into.
+extern "C" void tasr_debug_tc_trace(long long* dev_buf) { g_tc_trace = dev_buf; }
+
 // Launches logmel_tc_kernel over the batch (sub-batches of at most 1024 utterances / kListCapTc tiles per CTA).
 // Returns a negative value (and launches nothing) when the configuration is outside the kernel's scope.
 int tasr_logmel_tc_launch(const TasrFeaturizer* f, const tasr_lm::LogmelArgs& a_all, cudaStream_t st) {
@@ -635,7 +702,7 @@ int tasr_logmel_tc_launch(const TasrFeaturizer* f, const tasr_lm::LogmelArgs& a_
     attr_set[f->device] = true;
   }
   const int sms = sm_count();
-  const int tiles_per_row = (a_all.T_max + kTileFrames - 1) / kTileFrames;
+  const int tiles_per_row = (a_all.T_max + kTcFrames - 1) / kTcFrames;
   if (tiles_per_row > 0xffff) return -1;
   long long bmax = (long long)kListCapTc * sms / (tiles_per_row > 0 ? tiles_per_row : 1);
   if (bmax < 1) return -1;
@@ -645,6 +712,9 @@ int tasr_logmel_tc_launch(const TasrFeaturizer* f, const tasr_lm::LogmelArgs& a_
     TcArgs ta;
     ta.a = a_all;
     ta.dft32 = f->d_dft32;
+    static const int ablate = [] { const char* e = getenv("TASR_TC_ABLATE"); return e ? atoi(e) : 0; }();
+    ta.ablate = ablate;
+    ta.trace = g_tc_trace;
     ta.a.B = (a_all.B - b0 < bsub) ? a_all.B - b0 : bsub;
     ta.a.wav = a_all.wav + (size_t)b0 * a_all.row_stride;
     ta.a.len = a_all.len + b0;

@@ -1145,3 +1145,25 @@ def test_eager_pipeline_slot_reuse_keeps_lengths_of_in_flight_batches(cuda_devic
     for i in range(8):
         for g, w in zip(got[i], want[i]):
             assert torch.equal(g, w), i
+
+
+def test_logmel_tensor_core_kernel_opt_in(cuda_device):
+    """csrc/logmel_tc.cu (second FFT stage on tcgen05, opt-in with TASR_LOGMEL_TC=1 - the switch is read once per process,
+    hence the subprocess): same contract as the default kernel, checked by tools/tc_check.py against the float64 oracle on the
+    primary and the stress distributions, ragged lengths incl. 399 / 400 samples, collate padding exactly 0.0."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TASR_LOGMEL_TC="1")
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "tc_check.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    rows = re.findall(r"^(\w+)\s+lens=.*max\|err\|=([0-9.e+-]+) float32-oracle band=([0-9.e+-]+)", res.stdout, flags=re.M)
+    assert len(rows) == 6, res.stdout
+    for dist, err, band in rows:
+        err, band = float(err), float(band)
+        if dist in ("tilt", "half_silence", "zeros"):
+            assert err <= LOGMEL_TOL, (dist, err)
+        else:
+            assert err <= max(LOGMEL_TOL, STRESS_BAND * band), (dist, err, band)
