@@ -274,6 +274,35 @@ int tasr_audio_mask(const float* x, int64_t n, int32_t v, float pad_value, float
 int tasr_count_nonzero_frames(const float* feat, int32_t batch, int32_t t, int32_t f,
                               int32_t* n_frames, tasr_stream_t stream);
 
+/* First encoder block.  Replaces EncoderBlock.call (src/models/moonshine/encoder.py:151-154) =
+ * MHSAModule (src/models/layers/attention.py:519-602; MultiHeadAttention :44-230 with RoPE, positional_encoding.py:20-93)
+ * followed by FFNModule (src/models/layers/mlp.py:9-60), inference mode (dropout = identity):
+ *   q, k, v = x Wq, x Wk, x Wv (no bias); RoPE on q and k; softmax(q k^T / sqrt(head_dim) + (1 - mask) * -1e9) v; . Wo;
+ *   h1 = LayerNorm(x + .); out = LayerNorm(gelu(h1 W1 + b1) W2 + b2 + h1)       (exact-erf GELU, LayerNorm epsilon ln_eps).
+ * Weights float32 on the DEVICE in Keras shapes: wq / wk / wv [d_model, num_heads*head_dim], wo [num_heads*head_dim, d_model],
+ * w1 [d_model, d_model*fc_factor], b1 [d_model*fc_factor], w2 [d_model*fc_factor, d_model], b2 [d_model], LayerNorm gamma / beta
+ * [d_model].  The plan packs the four kernels as TF32 UMMA tiles; bias and LayerNorm pointers are borrowed (must outlive it).
+ * Built for the config/model.yaml shape: d_model 192 = 6 heads x 32 (rot_dim = max(head_dim // 2, 32) = head_dim), fc_factor 1..8;
+ * anything else returns TASR_ERR_UNSUPPORTED.  `MHSAModule.call` unpacks `inputs, pos = inputs` (attention.py:572) although
+ * EncoderBlock hands it one tensor; `pos` is unused by the 'sdpa' attention the encoder builds, so x is the whole [batch, t, d_model]
+ * tensor here (oracle/encoder_block_ref.py states the resolution).
+ * x [batch, t, d_model]; len [batch] device int32 = valid tokens per utterance (the padding mask of encoder.py:43-48 as a prefix
+ * length; NULL = no mask); workspace = tasr_encoder_block_workspace_floats(plan, batch, t) floats, 16-byte aligned; out [batch, t,
+ * d_model].  Rows t >= len[b] attend uniformly to all t keys, as the reference's float32 "-1e9" masking does.  Enqueue-only once
+ * tasr_encoder_block_prepare(plan, t_max) has sized the RoPE table (otherwise the first call with a larger t allocates). */
+typedef struct TasrEncoderBlockWeights {
+  const float *wq, *wk, *wv, *wo, *ln1_gamma, *ln1_beta, *w1, *b1, *w2, *b2, *ln2_gamma, *ln2_beta;
+  int32_t d_model, num_heads, head_dim, fc_factor;
+  float ln_eps;            /* tf.keras.layers.LayerNormalization default: 1e-3 */
+} TasrEncoderBlockWeights;
+typedef struct TasrEncoderBlockPlan TasrEncoderBlockPlan;
+int tasr_encoder_block_plan_create(const TasrEncoderBlockWeights* weights, TasrEncoderBlockPlan** out, tasr_stream_t stream);
+int tasr_encoder_block_plan_destroy(TasrEncoderBlockPlan* plan);
+int tasr_encoder_block_prepare(TasrEncoderBlockPlan* plan, int32_t t_max);
+int64_t tasr_encoder_block_workspace_floats(const TasrEncoderBlockPlan* plan, int32_t batch, int32_t t);
+int tasr_encoder_block_f32(TasrEncoderBlockPlan* plan, const float* x, const int32_t* len, int32_t batch, int32_t t,
+                           int32_t use_causal_mask, float* workspace, float* out, tasr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

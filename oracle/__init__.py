@@ -45,3 +45,9 @@ from .conv2d_subsampling_ref import (  # noqa: F401
 )
 from .synth import make_waveforms  # noqa: F401
 from . import specaugment_ref  # noqa: F401
+from .encoder_block_ref import (  # noqa: F401
+    rope_tables,
+    rope_apply,
+    encoder_block_ref,
+    glorot_encoder_block_weights,
+)

@@ -8,6 +8,7 @@ fails loudly without one."""
 from .speech_featurizer import SpeechFeaturizer, FeaturizerConfig  # noqa: F401
 from .subsampling import Conv1DSubsamplingLayer, get_conv_length  # noqa: F401
 from .conv2d_subsampling import Conv2dSubsampling  # noqa: F401
+from .encoder_block import EncoderBlock  # noqa: F401
 from .frontend import FrontEnd, ConformerFrontEnd, CapturedFrontEnd, InterleavedFrontEnd, REFERENCE_SPEECH_CONFIG, REFERENCE_SUBSAMPLING_CONFIG, load_reference_yaml  # noqa: F401
 from .collate import pack_waveforms, PinnedBatch, PackedBatch, shard_by_length  # noqa: F401
 

@@ -41,6 +41,11 @@ class TasrSepConvLayer(C.Structure):
     ]
 
 
+class TasrEncoderBlockWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("wq", "wk", "wv", "wo", "ln1_gamma", "ln1_beta", "w1", "b1", "w2", "b2", "ln2_gamma", "ln2_beta")] + [
+        ("d_model", C.c_int32), ("num_heads", C.c_int32), ("head_dim", C.c_int32), ("fc_factor", C.c_int32), ("ln_eps", C.c_float)]
+
+
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
 _SIGNATURES = {
     "tasr_version": (C.c_int, []),
@@ -79,6 +84,11 @@ _SIGNATURES = {
     "tasr_specaugment_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp]),
     "tasr_audio_mask": (C.c_int, [_vp, _i64, _i32, C.c_float, _vp, _vp]),
     "tasr_count_nonzero_frames": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "tasr_encoder_block_plan_create": (C.c_int, [C.POINTER(TasrEncoderBlockWeights), C.POINTER(_vp), _vp]),
+    "tasr_encoder_block_plan_destroy": (C.c_int, [_vp]),
+    "tasr_encoder_block_prepare": (C.c_int, [_vp, _i32]),
+    "tasr_encoder_block_workspace_floats": (C.c_int64, [_vp, _i32, _i32]),
+    "tasr_encoder_block_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
 }
 
 _lib = None

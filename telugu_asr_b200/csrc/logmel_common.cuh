@@ -79,8 +79,7 @@ __device__ __forceinline__ int pad_limit(int Tu, const LogmelArgs& a) {
 // weight); bin m-1 is complete when segment m ends.  Summation is in ascending k, like a dot product.
 template <int M, int M0, int M1>
 struct MelSeg {
-  static __device__ __forceinline__ void run(const float* __restrict__ Prow, const MelFixedW& w, float* __restrict__ srow,
-                                             float floor_, float scale, float acc_prev) {
+  static __device__ __forceinline__ void run(const float* __restrict__ Prow, const MelFixedW& w, float (&res)[M1 - M0], float acc_prev) {
     float acc_cur = 0.0f;
     constexpr int kBegin = kMelSegStart[M], kEnd = kMelSegStart[M + 1];
 #pragma unroll
@@ -89,14 +88,20 @@ struct MelSeg {
       if (M < M1) acc_cur = fmaf(p, w.wr[k], acc_cur);
       if (M > M0) acc_prev = fmaf(p, w.wf[k], acc_prev);
     }
-    if (M > M0) srow[M - 1] = lg2_normal(fmaxf(acc_prev, floor_)) * scale;
-    if constexpr (M < M1) MelSeg<M + 1, M0, M1>::run(Prow, w, srow, floor_, scale, acc_cur);
+    if constexpr (M > M0) res[M - 1 - M0] = acc_prev;
+    if constexpr (M < M1) MelSeg<M + 1, M0, M1>::run(Prow, w, res, acc_cur);
   }
 };
 
+// The sums of a group stay in registers until the whole group is done: a store to the staging row after every bin would fence
+// the loads of the power row behind it (both are shared memory), one exposed LDS latency per mel bin.
 template <int W>
 __device__ __forceinline__ void mel_fixed_group(const float* Prow, const MelFixedW& w, float* srow, float floor_, float scale) {
-  MelSeg<kMelGrp[W], kMelGrp[W], kMelGrp[W + 1]>::run(Prow, w, srow, floor_, scale, 0.0f);
+  constexpr int M0 = kMelGrp[W], M1 = kMelGrp[W + 1];
+  float res[M1 - M0];
+  MelSeg<M0, M0, M1>::run(Prow, w, res, 0.0f);
+#pragma unroll
+  for (int i = 0; i < M1 - M0; ++i) srow[M0 + i] = lg2_normal(fmaxf(res[i], floor_)) * scale;
 }
 
 

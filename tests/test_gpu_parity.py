@@ -53,25 +53,29 @@ def band_tol(wav, ln, ref64, p=None):
 
 
 def assert_logmel_parity(out, wav, ln):
-    """Primary distribution, any size, no outlier quota: EVERY value of an utterance within 1e-4 of the float64 oracle -
-    unless the float32 oracle itself is further than that from float64 on that very utterance (a near-cancelled mel bin:
-    configs[2] has one such value in 30 M, utterance 9 frame 87 bin 0, mel power 3e-7, where scipy's float32 evaluation
-    is 3.4e-4 off), in which case the stress rule applies to that utterance: STRESS_BAND x its float32 band.
+    """Primary distribution, any size: EVERY value of an utterance within 1e-4 of the float64 oracle - unless the float32
+    oracle itself is further than 1e-4 / STRESS_BAND from float64 on that very utterance (a near-cancelled mel bin: configs[2]
+    has such values, e.g. utterance 9 frame 87 bin 0, mel power 3e-7, where the float32 evaluation of the reference's own op
+    sequence is 3.4e-4 off), in which case the stress rule applies to that utterance: STRESS_BAND x its float32 band.  No quota
+    of utterances; what is bounded globally is the share of VALUES beyond 1e-4: fewer than one in a million.
     Returns the worst error and how many utterances needed the band."""
-    worst, n_band = 0.0, 0
+    worst, n_band, n_out, n_val = 0.0, 0, 0, 0
     for b in range(wav.shape[0]):
         r64 = oracle.logmel_ref(wav[b, : ln[b]], dtype=np.float64)
         T = r64.shape[0]
         if T == 0:
             continue
-        e = float(np.abs(out[b, :T, :, 0] - r64).max())
+        d = np.abs(out[b, :T, :, 0] - r64)
+        e = float(d.max())
+        n_val += d.size
         if e > LOGMEL_TOL:
             band = float(np.abs(oracle.logmel_ref(wav[b, : ln[b]], dtype=np.float32) - r64).max())
             assert band > LOGMEL_TOL / STRESS_BAND and e <= STRESS_BAND * band, (b, e, band)
             n_band += 1
+            n_out += int((d > LOGMEL_TOL).sum())
         worst = max(worst, e)
-    assert n_band <= max(1, wav.shape[0] // 100), n_band     # ... and that happens to at most one utterance in a hundred
-    return worst
+    assert n_out <= max(1, n_val // 1_000_000), (n_out, n_val, n_band)
+    return worst, n_band
 
 
 def test_native_library_is_loaded(cuda_device):
@@ -1167,3 +1171,70 @@ def test_logmel_tensor_core_kernel_opt_in(cuda_device):
             assert err <= LOGMEL_TOL, (dist, err)
         else:
             assert err <= max(LOGMEL_TOL, STRESS_BAND * band), (dist, err, band)
+
+
+@pytest.mark.parametrize("case", ["ragged", "no_mask", "fc2", "causal", "config3_shape"])
+def test_encoder_block_matches_oracle(cuda_device, case):
+    """EncoderBlock (src/models/moonshine/encoder.py:109-154) on the [B, T3, 192] tensor + lengths this path
+    produces, against oracle/encoder_block_ref.py (float64): max-abs error / max-abs reference <= 1e-3 on every valid row (TF32
+    dense layers), and the padded rows reproduce the reference's uniform attention."""
+    rng = np.random.default_rng(3)
+    B, T, fc, lens, causal = {"ragged": (5, 181, 1, [181, 120, 37, 1, 0], False), "no_mask": (3, 64, 1, None, False),
+                              "fc2": (2, 130, 2, [130, 77], False), "causal": (2, 70, 1, [70, 33], True),
+                              "config3_shape": (24, 181, 1, list(rng.integers(6, 182, 24)), False)}[case]
+    w = oracle.glorot_encoder_block_weights(192, 6, 32, fc, seed=13)
+    x = rng.standard_normal((B, T, 192)).astype(np.float32)
+    blk = tasr.EncoderBlock(input_dim=192, num_heads=6, head_dim=32, fc_factor=fc, activation="gelu", dropout=0.2)
+    blk.set_weights(w, cuda_device)
+    ln = None if lens is None else gpu(np.asarray(lens, dtype=np.int32), cuda_device)
+    out = blk(gpu(x, cuda_device), use_causal_mask=causal, lengths=ln)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    ref = oracle.encoder_block_ref(x, lens, w, 6, 32, dtype=np.float64, use_causal_mask=causal)
+    assert out.shape == ref.shape and np.isfinite(out).all()
+    scale = np.abs(ref).max()
+    L = [T] * B if lens is None else lens
+    for b in range(B):
+        if L[b]:
+            assert np.abs(out[b, :L[b]] - ref[b, :L[b]]).max() <= SUB_TOL_TF32 * scale, (case, b)
+        if L[b] < T and not causal:
+            assert np.abs(out[b, L[b]:] - ref[b, L[b]:]).max() <= SUB_TOL_TF32 * scale, (case, b, "padded rows")
+    if lens is not None:     # the float mask of Conv1DSubsamplingLayer.lengths_to_padding_mask gives the same result as the lengths
+        mask = (np.arange(T)[None, :] < np.asarray(lens)[:, None]).astype(np.float32)
+        out2 = blk(gpu(x, cuda_device), use_causal_mask=causal, mask=gpu(mask, cuda_device)).cpu().numpy()
+        np.testing.assert_array_equal(out2, out)
+
+
+def test_encoder_block_consumes_the_front_end_output(cuda_device):
+    """waveform -> FrontEnd -> EncoderBlock: the block takes `[B, T3, 192]` + `len3` exactly as the path delivers them."""
+    lens = [48000, 30000, 16000]
+    wav, ln = oracle.make_waveforms(lens, seed=5, dist="tilt")
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    fe = tasr.FrontEnd(math="tf32")
+    fe.set_weights(weights, cuda_device)
+    out, mask, len3 = fe(gpu(wav, cuda_device), gpu(ln, cuda_device))[:3]
+    w = oracle.glorot_encoder_block_weights(192, 6, 32, 1, seed=13)
+    blk = tasr.EncoderBlock(input_dim=192, num_heads=6, head_dim=32, fc_factor=1)
+    blk.set_weights(w, cuda_device)
+    y = blk(out, mask=mask)
+    torch.cuda.synchronize()
+    ref = oracle.encoder_block_ref(out.cpu().numpy(), len3.cpu().numpy(), w, 6, 32, dtype=np.float64)
+    y = y.cpu().numpy()
+    for b, L in enumerate(len3.cpu().numpy()):
+        assert np.abs(y[b, :L] - ref[b, :L]).max() <= SUB_TOL_TF32 * np.abs(ref).max()
+
+
+def test_encoder_block_error_behaviour(cuda_device):
+    with pytest.raises(NotImplementedError):
+        tasr.EncoderBlock(input_dim=192, num_heads=6, head_dim=32, activation="swiglu")
+    blk = tasr.EncoderBlock(input_dim=288, num_heads=8, head_dim=36)          # the reference's constructor defaults
+    with pytest.raises(NotImplementedError):                                  # ... are outside the built shape
+        blk.build(cuda_device)
+    blk = tasr.EncoderBlock(input_dim=192, num_heads=6, head_dim=32)
+    blk.build(cuda_device, seed=1)
+    with pytest.raises(ValueError):
+        blk(torch.zeros((2, 5, 80), device=cuda_device))
+    with pytest.raises(NotImplementedError):
+        blk(torch.zeros((2, 5, 192), device=cuda_device), training=True)
+    with pytest.raises(RuntimeError):
+        blk(torch.zeros((2, 5, 192)))
