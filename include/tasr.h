@@ -73,7 +73,8 @@ typedef struct TasrSepConvLayer {
   int32_t c_out;
   int32_t kernel;     /* 9 */
   int32_t stride;     /* 2 */
-  int32_t same;       /* 0 = "valid" (config/model.yaml:26); 1 = "same" is TASR_ERR_UNSUPPORTED in the conv kernels */
+  int32_t same;       /* 0 = "valid" (config/model.yaml:26); 1 = "same" (the reference constructor's default, encoder.py:24;
+                         TensorFlow's rule for the tensor length t_in): dense entry points only, the ragged ones refuse it */
   int32_t activation; /* TASR_ACT_* */
 } TasrSepConvLayer;
 

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtasr_b200.so")
 STAMP = os.path.join(HERE, ".libtasr_b200.stamp")
-SOURCES = ["api.cu", "absmax.cu", "conv2d_subsample.cu", "encoder_block.cu", "feature_post.cu", "ingest.cu", "logmel.cu", "logmel_tc.cu", "sepconv_fp32.cu", "sepconv_tf32.cu", "sepconv_ws.cu", "specaugment.cu"]
+SOURCES = ["api.cu", "absmax.cu", "conv2d_subsample.cu", "encoder_block.cu", "feature_post.cu", "ingest.cu", "logmel.cu", "logmel_generic.cu", "logmel_tc.cu", "sepconv_fp32.cu", "sepconv_tf32.cu", "sepconv_ws.cu", "specaugment.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

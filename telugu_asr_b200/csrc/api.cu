@@ -48,17 +48,23 @@ extern "C" int tasr_featurizer_create(const TasrFeatParams* p, const float* hann
                                       const float* mel_w_host, TasrFeaturizer** out) {
   if (!p || !hann_host || !mel_w_host || !out) return fail(TASR_ERR_BAD_ARG, "tasr_featurizer_create: null argument");
   *out = nullptr;
-  if (p->frame_length != kFrameLen || p->frame_step != kFrameStep || p->fft_length != kFft ||
-      p->num_mel_bins != kMel)
-    return fail(TASR_ERR_UNSUPPORTED,
-                "tasr_featurizer_create: kernels are specialised for frame_length=400, frame_step=160, "
-                "fft_length=512, num_mel_bins=80 (config/model.yaml); got %d/%d/%d/%d",
-                p->frame_length, p->frame_step, p->fft_length, p->num_mel_bins);
   if (p->feature_type < TASR_FEAT_LOG_MEL || p->feature_type > TASR_FEAT_WAVEFORM)
     return fail(TASR_ERR_BAD_ARG, "tasr_featurizer_create: unknown feature_type %d", p->feature_type);
   if (!(p->output_floor > 0.0f)) return fail(TASR_ERR_BAD_ARG, "tasr_featurizer_create: output_floor must be > 0");
   if (p->output_floor < 1.17549435e-38f)
     return fail(TASR_ERR_UNSUPPORTED, "tasr_featurizer_create: output_floor below FLT_MIN (the log uses a flush-to-zero MUFU)");
+  if (p->frame_length != kFrameLen || p->frame_step != kFrameStep || p->fft_length != kFft || p->num_mel_bins != kMel) {
+    // Off the specialised geometry (config/model.yaml: 25 ms / 10 ms at 16 kHz, 80 bins): the general kernel of logmel_generic.cu
+    TasrFeaturizer* f = new TasrFeaturizer();
+    memset(f, 0, sizeof(*f));
+    f->p = *p;
+    f->log_scale = p->log_base_e ? 0.69314718055994530942f : 0.30102999566398119521f;
+    int rc = tasr_logmel_generic_create(f, hann_host, mel_w_host);      // validates the geometry before touching the device
+    if (rc == TASR_OK) rc = check_cuda(cudaGetDevice(&f->device), "cudaGetDevice");
+    if (rc != TASR_OK) { tasr_featurizer_destroy(f); return rc; }
+    *out = f;
+    return TASR_OK;
+  }
 
   // Banded mel structure from the dense matrix the caller built (values are used verbatim).
   MelBands bands;
@@ -146,6 +152,9 @@ extern "C" int tasr_featurizer_destroy(TasrFeaturizer* f) {
   cudaFree(f->d_bands);
   cudaFree(f->d_dct);
   cudaFree(f->d_dft32);
+  cudaFree(f->d_gwin);
+  cudaFree(f->d_gmel);
+  cudaFree(f->d_gtw);
   delete f;
   return TASR_OK;
 }

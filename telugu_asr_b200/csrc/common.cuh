@@ -86,11 +86,21 @@ struct TasrFeaturizer {
   int mel_fixed;        // 1: the matrix has the compiled-in config/model.yaml structure (mel_geometry.inc)
   float mel_fixed_w[512];  // wr[256] | wf[256], per FFT bin (kernel-parameter constants of the unrolled projection)
   unsigned char* d_dft32;  // [16 KB] UMMA B images of the DFT-32 matrix, FP16 high | low parts (logmel_tc.cu)
+  // any other frame geometry (logmel_generic.cu): window [frame_length], dense mel matrix [fft/2+1, n_mel], twiddles [fft/2]
+  int generic, g_log2fft;
+  float* d_gwin;
+  float* d_gmel;
+  float2* d_gtw;
 };
 
 // feature_post.cu: mfcc DCT and/or per-frame z-score / min-max normalisation, in place on [B, T_max, 80].
 int tasr_feature_post_launch(const TasrFeaturizer* f, float* feat, const int32_t* n_frames, int32_t B, int32_t T_max,
                              cudaStream_t st);
+
+// logmel_generic.cu: featurizer for frame geometries other than 400 / 160 / 512 / 80
+int tasr_logmel_generic_create(TasrFeaturizer* f, const float* hann_host, const float* mel_w_host);
+int tasr_logmel_generic_launch(const TasrFeaturizer* f, const float* wav, const int32_t* len, const float* peak, int32_t B,
+                               int64_t row_stride, float* out, int32_t T_max, int32_t* n_frames, cudaStream_t st);
 
 // logmel_tc.cu: host builder of the DFT-32 operand images (16 KB)
 void tasr_logmel_tc_build_dft32(unsigned char* img16k);

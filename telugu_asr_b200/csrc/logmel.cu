@@ -439,6 +439,10 @@ static int logmel_launch(const TasrFeaturizer* f, const float* wav, const int32_
   int dev = 0;
   TASR_CUDA(cudaGetDevice(&dev));
   if (dev != f->device) return fail(TASR_ERR_BAD_ARG, "tasr_logmel_f32: featurizer was created on device %d, current device is %d", f->device, dev);
+  if (f->generic) {     // any other frame geometry: the general kernel (writes every padding row; no single-pass mode)
+    if (peak_out) return fail(TASR_ERR_UNSUPPORTED, "tasr_logmel_f32_single_pass: built for the 400/160/512/80 geometry only");
+    return tasr_logmel_generic_launch(f, wav, len, peak, B, row_stride, out, T_max, n_frames, st);
+  }
 
   const int tiles_per_row = (T_max + kTileFrames - 1) / kTileFrames;
   const long long total = (long long)tiles_per_row * B;

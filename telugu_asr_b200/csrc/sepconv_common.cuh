@@ -245,7 +245,17 @@ struct SepArgs {
   // max(x + in_scale2 * lg2(1 / (in_peak[b] + 1e-9)), in_floor)
   const float* in_peak;
   float in_scale2, in_floor;
+  // padding = "same" (dense mode only): output frame t reads input rows 2t + k + row_off, row_off = -pad_left of TensorFlow's
+  // SAME rule for the tensor length T_in; rows outside [0, T_in) are zero.  0 for "valid".
+  int32_t row_off;
 };
+
+// TensorFlow SAME padding before the first row: out = ceil(T/s), total = max((out-1) s + k - T, 0), left = total / 2.
+inline int tasr_same_pad_left(int T, int k, int s) {
+  const int out = (T + s - 1) / s;
+  const int total = (out - 1) * s + k - T;
+  return total > 0 ? total / 2 : 0;
+}
 
 }  // namespace tasr_sep
 

@@ -9,7 +9,7 @@
 // CTA tile: 64 output frames x 64 output channels, 256 threads with a 4x4 register tile each,
 // input channels consumed in chunks of 16: stage x rows -> depthwise into Ys[c][t] ->
 // rank-16 update from Ys and the pointwise chunk Ws[c][o].
-#include "common.cuh"
+#include "sepconv_common.cuh"
 
 using namespace tasr;
 
@@ -33,7 +33,7 @@ template <int K, int STRIDE>
 __global__ void __launch_bounds__(kThreads)
 sepconv_fp32_kernel(const float* __restrict__ x, int T_in, int C_in, const float* __restrict__ dw,
                     const float* __restrict__ pw, const float* __restrict__ bias, int C_out, int act,
-                    float* __restrict__ y, int T_out) {
+                    float* __restrict__ y, int T_out, int row_off) {
   constexpr int XR = (TO - 1) * STRIDE + K;   // input rows per tile (135)
   __shared__ __align__(16) float Xs[XR][KC + 1];
   __shared__ __align__(16) float Ys[KC][TO + 4];
@@ -57,8 +57,8 @@ sepconv_fp32_kernel(const float* __restrict__ x, int T_in, int C_in, const float
     // stage x[2*t0 .. 2*t0+XR) x [c0, c0+16), depthwise taps and the pointwise chunk
     for (int i = tid; i < XR * KC; i += kThreads) {
       const int r = i / KC, c = i - r * KC;
-      const int tg = t0 * STRIDE + r;
-      Xs[r][c] = (tg < T_in && c0 + c < C_in) ? xb[(size_t)tg * C_in + c0 + c] : 0.0f;
+      const int tg = t0 * STRIDE + r + row_off;     // row_off = -pad_left for padding='same': rows outside the tensor are zero
+      Xs[r][c] = (tg >= 0 && tg < T_in && c0 + c < C_in) ? xb[(size_t)tg * C_in + c0 + c] : 0.0f;
     }
     for (int i = tid; i < K * KC; i += kThreads) {
       const int k = i / KC, c = i - k * KC;
@@ -125,12 +125,12 @@ int validate_sepconv(const char* who, const void* x, int32_t B, int32_t T_in, co
   if (!x || !L || !y) return fail(TASR_ERR_BAD_ARG, "%s: null argument", who);
   if (!L->dw || !L->pw || !L->bias) return fail(TASR_ERR_BAD_ARG, "%s: null weight pointer", who);
   if (B < 0 || T_in < 0 || T_out < 0 || L->c_in < 1 || L->c_out < 1) return fail(TASR_ERR_BAD_ARG, "%s: bad shape", who);
-  if (L->kernel != 9 || L->stride != 2 || L->same)
-    return fail(TASR_ERR_UNSUPPORTED, "%s: kernels are built for kernel=9, stride=2, padding='valid' (config/model.yaml:24-26); got k=%d s=%d same=%d",
-                who, L->kernel, L->stride, L->same);
+  if (L->kernel != 9 || L->stride != 2)
+    return fail(TASR_ERR_UNSUPPORTED, "%s: kernels are built for kernel=9, stride=2 (config/model.yaml:24-25); got k=%d s=%d",
+                who, L->kernel, L->stride);
   if (L->activation < TASR_ACT_NONE || L->activation > TASR_ACT_RELU) return fail(TASR_ERR_BAD_ARG, "%s: unknown activation %d", who, L->activation);
-  const int32_t t_full = (T_in >= L->kernel) ? (T_in - L->kernel) / L->stride + 1 : 0;
-  if (T_out > t_full) return fail(TASR_ERR_BAD_ARG, "%s: t_out=%d exceeds the valid conv length %d of t_in=%d", who, T_out, t_full, T_in);
+  const int32_t t_full = L->same ? (T_in + L->stride - 1) / L->stride : ((T_in >= L->kernel) ? (T_in - L->kernel) / L->stride + 1 : 0);
+  if (T_out > t_full) return fail(TASR_ERR_BAD_ARG, "%s: t_out=%d exceeds the %s conv length %d of t_in=%d", who, T_out, L->same ? "same" : "valid", t_full, T_in);
   if (!aligned16(x) || !aligned16(y)) return fail(TASR_ERR_MISALIGNED, "%s: x/y must be 16-byte aligned", who);
   if (B > 65535) return fail(TASR_ERR_UNSUPPORTED, "%s: batch > 65535", who);
   return TASR_OK;
@@ -144,7 +144,8 @@ extern "C" int tasr_sepconv1d_f32(const float* x, int32_t B, int32_t T_in, const
   if (B == 0 || T_out == 0) return TASR_OK;
   dim3 grid((T_out + TO - 1) / TO, (L->c_out + CT - 1) / CT, B);
   sepconv_fp32_kernel<9, 2><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-      x, T_in, L->c_in, L->dw, L->pw, L->bias, L->c_out, L->activation, y, T_out);
+      x, T_in, L->c_in, L->dw, L->pw, L->bias, L->c_out, L->activation, y, T_out,
+      L->same ? -tasr_sep::tasr_same_pad_left(T_in, L->kernel, L->stride) : 0);
   TASR_LAUNCH_CHECK("sepconv_fp32_kernel");
   return TASR_OK;
 }

@@ -97,9 +97,9 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
   const float* bsrc = a.bpack + (size_t)nh * a.n_chunks * NT * kKC;
   const uint32_t idesc = umma_idesc_tf32(kMT, NT);
   const int tw = t0 + warp * kRun;       // first output frame of this warp's run
-  const int r0 = 2 * tw;                 // first input row of the run
-  const float* xrow = a.x + ((size_t)b * a.T_in + r0) * C_in + lane;
-  const bool run_inside = (r0 + kWin <= a.T_in);   // warp-uniform: no row of this run is past the input
+  const int r0 = 2 * tw + a.row_off;     // first input row of the run (row_off = -pad_left for padding='same', else 0)
+  const float* xrow = a.x + ((long long)b * a.T_in + r0) * C_in + lane;
+  const bool run_inside = (r0 >= 0 && r0 + kWin <= a.T_in);   // warp-uniform: no row of this run is outside the input
   // Ragged mode: a run that starts in the padding produces only the constant row; its depthwise work is
   // skipped (its A rows stay stale — every output row depends on its own A row only) and the epilogue
   // writes the constant row for those frames.
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 2) sepconv_tf32_kernel(const SepArgs
     } else {
 #pragma unroll
       for (int i = 0; i < kWin; ++i)
-        v[i] = (cok && r0 + i < a.T_in) ? __ldg(xrow + c0 + (size_t)i * C_in) : 0.0f;
+        v[i] = (cok && r0 + i >= 0 && r0 + i < a.T_in) ? __ldg(xrow + c0 + (long long)i * C_in) : 0.0f;
 #pragma unroll
       for (int k = 0; k < 9; ++k) w[k] = cok ? __ldg(a.dw + k * C_in + c0 + lane) : 0.0f;
     }
@@ -281,9 +281,9 @@ extern "C" int tasr_sepconv_plan_create(const TasrSepConvLayer* L, TasrSepConvPl
   if (!L || !out) return fail(TASR_ERR_BAD_ARG, "tasr_sepconv_plan_create: null argument");
   *out = nullptr;
   if (!L->dw || !L->pw || !L->bias) return fail(TASR_ERR_BAD_ARG, "tasr_sepconv_plan_create: null weight pointer");
-  if (L->kernel != 9 || L->stride != 2 || L->same)
-    return fail(TASR_ERR_UNSUPPORTED, "tasr_sepconv_plan_create: kernels are built for kernel=9, stride=2, padding='valid'; got k=%d s=%d same=%d",
-                L->kernel, L->stride, L->same);
+  if (L->kernel != 9 || L->stride != 2)
+    return fail(TASR_ERR_UNSUPPORTED, "tasr_sepconv_plan_create: kernels are built for kernel=9, stride=2; got k=%d s=%d",
+                L->kernel, L->stride);
   if (L->activation < TASR_ACT_NONE || L->activation > TASR_ACT_RELU)
     return fail(TASR_ERR_BAD_ARG, "tasr_sepconv_plan_create: unknown activation %d", L->activation);
   if (L->c_in < 8 || (L->c_in & 7))
@@ -359,6 +359,14 @@ static int launch_tf32(const char* who, const TasrSepConvPlan* p, const float* x
   a.in_peak = gain ? gain->peak : nullptr;
   a.in_scale2 = gain ? gain->log_scale_x2 : 0.0f;
   a.in_floor = gain ? gain->log_floor : 0.0f;
+  a.row_off = 0;
+  if (p->L.same) {
+    // padding='same' (the reference constructor's default, encoder.py:24): dense mode only — the ragged bookkeeping
+    // (constant padding rows, tiles skipped by length) is written for 'valid' receptive fields
+    if (len0 != nullptr)
+      return fail(TASR_ERR_UNSUPPORTED, "%s: padding='same' layers run in dense mode (tasr_sepconv1d_tf32), not ragged", who);
+    a.row_off = -tasr_same_pad_left(T_in, p->L.kernel, p->L.stride);
+  }
   if (p->use_ws) {
     const int wrc = tasr_sepconv_ws_launch(p, a, B, (cudaStream_t)stream);
     if (wrc >= 0) return wrc;            // launched (TASR_OK) or failed with an error code

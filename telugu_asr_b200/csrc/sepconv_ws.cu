@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) sepconv_ws_kernel(const __grid_
       int g = 0;
       for (int k = 0; k < n_c; ++k) {
         const int item = list_c[k];
-        const int b = item >> 16, row0 = 2 * ((item >> 4) & 0xfff) * kMT;
+        const int b = item >> 16, row0 = 2 * ((item >> 4) & 0xfff) * kMT + a.row_off;   // (negative / past-the-end rows arrive as zeros)
         for (int kc = 0; kc < n_chunks; ++kc, ++g) {
           const int s = g % kStagesX, n = g / kStagesX;
           if (n > 0) mbar_wait(bar_xempty(s), (n - 1) & 1);

@@ -45,8 +45,13 @@ def load_reference_yaml(path: str):
 class FrontEnd:
     def __init__(self, speech_config: dict | None = None, subsampling_config: dict | None = None,
                  model_dim: int = REFERENCE_D_MODEL, math: str = "tf32", device=None, seed: int = 0,
-                 lean_intermediates: bool = True, single_pass: bool = True):
+                 lean_intermediates: bool = True, single_pass: bool = True, assume_collated: bool = True):
         self.featurizer = SpeechFeaturizer(**(speech_config or REFERENCE_SPEECH_CONFIG))
+        # The reference's batches come out of `padded_batch` (src/dataset.py:236-252): padded to their longest utterance,
+        # so max(lengths) == N_max and every shape of the step (T_max, the mask width max(len3)) follows from the tensor
+        # shape on the host.  With assume_collated=True a call without `max_length` takes N_max for it and only enqueues;
+        # False restores the data-dependent mask width for over-padded batches (one device->host read of max(len3)).
+        self.assume_collated = bool(assume_collated)
         self.subsampling = Conv1DSubsamplingLayer(
             model_dim=model_dim, subsampling_config=subsampling_config or REFERENCE_SUBSAMPLING_CONFIG,
             input_dim=self.featurizer.num_feature_bins, math=math, seed=seed, name="asr_encoder_conv_subsampling")
@@ -74,6 +79,8 @@ class FrontEnd:
         feature tensor is then padded to exactly the batch maximum and the mask width is derived
         on the host, so the step enqueues without any device->host synchronisation."""
         t_max = None
+        if max_length is None and (lengths is None or self.assume_collated):
+            max_length = int(wav.shape[1])
         if max_length is not None:
             t_max = max(0, int(self.featurizer.get_nframes(int(max_length))))
         sub = self.subsampling

@@ -108,11 +108,8 @@ class SpeechFeaturizer:
     def _check_supported(self):
         if self.padding and self.padding > 0:
             raise NotImplementedError("padding > 0 (0.0 in config/model.yaml:17; the reference branch fails on 1-D input)")
-        if self.feature_type != "waveform" and (self.frame_length, self.frame_step, self.num_feature_bins) != (400, 160, 80):
-            raise NotImplementedError(
-                "the B200 kernels are specialised for 25 ms / 10 ms frames at 16 kHz and 80 feature bins "
-                f"(config/model.yaml:1-5); got frame_length={self.frame_length}, frame_step={self.frame_step}, "
-                f"num_feature_bins={self.num_feature_bins}")
+        # (frame geometries other than config/model.yaml's 400 / 160 / 512 / 80 run on the general kernel of
+        #  csrc/logmel_generic.cu: log-mel and spectrogram, no mfcc / per-frame normalisation, no single-pass mode)
 
     def _handle(self, device: torch.device) -> int:
         idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -221,8 +218,11 @@ class SpeechFeaturizer:
         out = out[:, :n_max]
         return out[0] if one else out
 
+    def is_reference_geometry(self) -> bool:
+        return (self.frame_length, self.frame_step, self.fft_length, self.num_feature_bins) == (400, 160, 512, 80)
+
     def supports_single_pass(self) -> bool:
-        return bool(self._normalize_signal and not self.pad_end and not self._normalize_zscore and not self._normalize_min_max
+        return bool(self.is_reference_geometry() and self._normalize_signal and not self.pad_end and not self._normalize_zscore and not self._normalize_min_max
                     and self.feature_type in (FeaturizerConfig.log_mel_spectrogram, FeaturizerConfig.spectrogram))
 
     def apply_deferred_gain(self, raw: torch.Tensor, n_frames: torch.Tensor, gain: "DeferredGain") -> torch.Tensor:

@@ -306,7 +306,10 @@ class Conv1DSubsamplingLayer:
             side_result = self._lengths_on_side_stream(lengths, max_frames)
 
         use_tf32 = self.math == "tf32"
-        if input_gain is not None and not (use_tf32 and prefix_lengths and self.assume_zero_padding):
+        # the ragged kernels (constant padding rows, tiles skipped by length) are written for 'valid' receptive fields;
+        # a stack with a padding='same' layer (the reference constructor's default, encoder.py:24) runs dense
+        all_valid = all(p == "valid" for p in self.padding)
+        if input_gain is not None and not (use_tf32 and prefix_lengths and self.assume_zero_padding and all_valid):
             raise ValueError("input_gain needs the ragged TF32 path: math='tf32', assume_zero_padding=True and mask=n_frames [B]")
         if use_tf32:
             self._ensure_plans()
@@ -314,13 +317,13 @@ class Conv1DSubsamplingLayer:
             st = _native.stream_ptr()
             t_in = T
             for i in range(len(self.kernel_size)):
-                if self.padding[i] != "valid":
-                    raise NotImplementedError("padding='same' convs are not built (config/model.yaml:26 uses 'valid')")
-                t_out = max(0, get_conv_length(t_in, self.kernel_size[i], "valid", self.strides[i]))
+                if self.padding[i] not in ("valid", "same"):
+                    raise ValueError(f"padding must be 'valid' or 'same', got {self.padding[i]!r}")
+                t_out = max(0, get_conv_length(t_in, self.kernel_size[i], self.padding[i], self.strides[i]))
                 cout = self.filters[i]
                 y = _native.empty((B, t_out, cout), torch.float32, x.device)
                 if B and t_out:
-                    if use_tf32 and prefix_lengths and self.assume_zero_padding:
+                    if use_tf32 and prefix_lengths and self.assume_zero_padding and all_valid:
                         lean_i = lean_intermediates and i + 1 < len(self.kernel_size)
                         gain_i = input_gain if i == 0 else None
                         if lean_i or gain_i is not None:

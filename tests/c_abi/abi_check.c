@@ -68,7 +68,7 @@ int main(int argc, char** argv) {
   /* a frame geometry the kernels are not built for is TASR_ERR_UNSUPPORTED at handle creation */
   TasrFeatParams p;
   memset(&p, 0, sizeof(p));
-  p.sample_rate = 16000; p.frame_length = 320; p.frame_step = 160; p.fft_length = 512; p.num_mel_bins = 80;
+  p.sample_rate = 16000; p.frame_length = 320; p.frame_step = 160; p.fft_length = 500; p.num_mel_bins = 80;   /* fft_length must be a power of two */
   p.preemphasis = 0.97f; p.output_floor = 1e-9f;
   static float hann[400], mel[257 * 80];
   TasrFeaturizer* f = 0;

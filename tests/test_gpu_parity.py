@@ -1238,3 +1238,89 @@ def test_encoder_block_error_behaviour(cuda_device):
         blk(torch.zeros((2, 5, 192), device=cuda_device), training=True)
     with pytest.raises(RuntimeError):
         blk(torch.zeros((2, 5, 192)))
+
+
+@pytest.mark.parametrize("math,tol", [("fp32", SUB_TOL_FP32), ("tf32", SUB_TOL_TF32)])
+@pytest.mark.parametrize("padding", [["same", "same", "same"], ["same", "valid", "same"]])
+def test_subsampling_same_padding(cuda_device, math, tol, padding):
+    """padding='same' is the reference constructor's default (encoder.py:24): TensorFlow's SAME rule for the tensor length
+    (ceil(T/2) frames; 7 or 8 zero rows split before / after, the odd one after), lengths through ceil(L/2)
+    (src/utils/math_util.py:27-28).  Even and odd T, model_dim 192 and the constructor's default 288."""
+    rng = np.random.default_rng(4)
+    for model_dim, T, lens in ((192, 301, [301, 120, 9, 1]), (288, 128, [128, 77])):
+        cfg = dict(tasr.REFERENCE_SUBSAMPLING_CONFIG, padding=padding)
+        weights = oracle.glorot_subsampling_weights(model_dim, 80, seed=7)
+        layer = tasr.Conv1DSubsamplingLayer(model_dim, cfg, math=math)
+        layer.set_weights(weights, cuda_device)
+        feat = rng.standard_normal((len(lens), T, 80, 1)).astype(np.float32)
+        for b, L in enumerate(lens):
+            feat[b, L:] = 0.0
+        out, mask, len_all = layer(gpu(feat, cuda_device), mask=gpu(np.asarray(lens, np.int32), cuda_device), return_lengths=True)
+        torch.cuda.synchronize()
+        ref_out, ref_mask, ref_len = oracle.subsample_ref(feat, np.asarray(lens), weights, activations=tuple(layer.activations), padding=tuple(padding),
+                                                          dtype=np.float64)
+        out = out.cpu().numpy()
+        assert out.shape == ref_out.shape
+        np.testing.assert_array_equal(len_all.cpu().numpy(), ref_len)
+        np.testing.assert_array_equal(mask.cpu().numpy(), ref_mask)
+        assert np.abs(out - ref_out).max() <= tol * np.abs(ref_out).max(), (model_dim, np.abs(out - ref_out).max())
+
+
+@pytest.mark.parametrize("cfg", [dict(sample_rate=8000, frame_ms=32, stride_ms=16, num_feature_bins=40, upper_edge_hertz=4000.0),
+                                 dict(sample_rate=16000, frame_ms=20, stride_ms=10, num_feature_bins=64),
+                                 dict(sample_rate=22050, frame_ms=25, stride_ms=10, num_feature_bins=80, upper_edge_hertz=11025.0, pad_end=True),
+                                 dict(sample_rate=16000, frame_ms=25, stride_ms=10, num_feature_bins=128, feature_type="spectrogram", log_base="e")])
+def test_featurizer_other_frame_geometries(cuda_device, cfg):
+    """SpeechFeaturizer derives frame_length / frame_step from arbitrary sample_rate / frame_ms / stride_ms
+    (src/speech_featurizer.py:46-49) and tf.signal.stft pads to the enclosing power of two: anything other than the
+    config/model.yaml geometry runs on the general kernel (csrc/logmel_generic.cu) and is checked against the oracle."""
+    full = dict(tasr.REFERENCE_SPEECH_CONFIG)
+    full.update(cfg)
+    feat = tasr.SpeechFeaturizer(**full)
+    p = oracle.FeatParams(**{k: v for k, v in full.items() if k in oracle.FeatParams.__dataclass_fields__})
+    assert (feat.frame_length, feat.frame_step, feat.fft_length) == (p.frame_length, p.frame_step, p.fft_length)
+    assert not feat.is_reference_geometry() and not feat.supports_single_pass()
+    lens = [3 * full["sample_rate"] // 2, feat.frame_length, feat.frame_length - 1, 5000, 0]
+    wav, ln = oracle.make_waveforms(lens, seed=21, dist="tilt", sample_rate=full["sample_rate"])
+    out, nf = feat(gpu(wav, cuda_device), gpu(ln, cuda_device))
+    torch.cuda.synchronize()
+    out, nf = out.cpu().numpy(), nf.cpu().numpy()
+    ref64, nref = oracle.logmel_batch_ref(wav, ln, p, dtype=np.float64)
+    np.testing.assert_array_equal(nf, nref)
+    assert out.shape == ref64.shape
+    tol = band_tol(wav, ln, ref64, p)
+    assert np.abs(out - ref64).max() <= tol, np.abs(out - ref64).max()
+    for b, t in enumerate(nf):
+        assert not out[b, t:].any()
+    one = feat(gpu(wav[0, : lens[0]].copy(), cuda_device)).cpu().numpy()     # the reference's 1-D call (src/dataset.py:171)
+    np.testing.assert_array_equal(one, out[0, : nf[0], :, 0])
+
+
+def test_front_end_call_without_max_length_only_enqueues(cuda_device):
+    """The reference-signature call (no `max_length`) of a collated batch derives every shape on the host: no device->host
+    copy, no allocator call that synchronises - checked with torch's sync debug mode; an over-padded batch with
+    assume_collated=False still gets the reference's mask width max(len3) (encoder.py:44)."""
+    lens = [48000, 30000, 16000]
+    wav, ln = oracle.make_waveforms(lens, seed=5, dist="tilt")
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    fe = tasr.FrontEnd(math="tf32")
+    fe.set_weights(weights, cuda_device)
+    w, l = gpu(wav, cuda_device), gpu(ln, cuda_device)
+    want = fe(w, l, max_length=int(ln.max()))
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        got = fe(w, l)
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    over = np.zeros((3, 64000), dtype=np.float32)
+    over[:, :48000] = wav
+    fe2 = tasr.FrontEnd(math="tf32", assume_collated=False)
+    fe2.set_weights(weights, cuda_device)
+    o2, m2, l2 = fe2(gpu(over, cuda_device), l)
+    assert m2.shape[1] == int(l2.max()) == want[1].shape[1] and torch.equal(m2, want[1]) and torch.equal(l2, want[2])
+    L3 = int(l2.max())
+    assert torch.equal(o2[:, :L3], want[0][:, :L3])

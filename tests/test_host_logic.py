@@ -43,7 +43,7 @@ def test_c_abi_argument_errors_without_gpu():
     assert b"null" in lib.tasr_last_error()
     hann = tables.hann_window_f32(400)
     mel = tables.mel_weight_matrix_f32(80, 257, 16000, 0.0, 8000.0)
-    bad = _native.TasrFeatParams(16000, 320, 160, 512, 80, 1, 0, 0, 0.97, 1e-9)
+    bad = _native.TasrFeatParams(16000, 320, 160, 500, 80, 1, 0, 0, 0.97, 1e-9)     # fft_length is not a power of two
     rc = lib.tasr_featurizer_create(ctypes.byref(bad), hann.ctypes.data_as(ctypes.c_void_p),
                                     mel.ctypes.data_as(ctypes.c_void_p), ctypes.byref(out))
     assert rc == _native.TASR_ERR_UNSUPPORTED
