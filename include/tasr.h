@@ -111,6 +111,13 @@ int tasr_unpack_f32(const float* packed, const int64_t* offset, const int32_t* l
 int tasr_unpack_pcm16(const int16_t* packed, const int64_t* offset, const int32_t* len, int32_t batch,
                       int32_t max_len, float* wav, int64_t row_stride, tasr_stream_t stream);
 
+/* The way back of the device collate: x [batch, t, c] whose rows t >= len[b] are collate padding -> packed [sum_b len[b], c]
+ * (utterance b at row offset[b]; offset has batch + 1 entries, the last is the total; int64, device).  A consumer that reads
+ * only valid rows (src/models/moonshine/encoder.py:237-247 masks the rest) can fetch the packed rows instead of the padded
+ * tensor: about half the device->host bytes on a ragged batch.  packed must hold sum_b min(len[b], t) rows; c % 4 == 0. */
+int tasr_pack_valid_rows(const float* x, const int32_t* len, int32_t batch, int32_t t, int32_t c, float* packed,
+                         int64_t* offset, tasr_stream_t stream);
+
 /* Replaces tf.reduce_max(tf.abs(signal)) (src/speech_featurizer.py:70), batched:
  * peak[b] = max_{n < len[b]} |wav[b*row_stride + n]|.  peak is overwritten. */
 int tasr_absmax_f32(const float* wav, const int32_t* len, int32_t batch, int64_t row_stride,

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "tasr_featurizer_uses_fixed_mel": (C.c_int, [_vp]),
     "tasr_unpack_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     "tasr_unpack_pcm16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "tasr_pack_valid_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "tasr_waveform_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "tasr_absmax_f32": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "tasr_logmel_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _vp, _vp]),

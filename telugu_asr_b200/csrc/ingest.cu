@@ -96,3 +96,55 @@ extern "C" int tasr_unpack_pcm16(const int16_t* packed, const int64_t* offset, c
                                  int32_t max_len, float* wav, int64_t row_stride, tasr_stream_t stream) {
   return unpack_common("tasr_unpack_pcm16", true, packed, offset, len, B, max_len, wav, row_stride, stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Valid rows only on the way back (the other end of the device collate): x [B, T, C] with a valid prefix of len[b] rows per
+// utterance -> packed [sum_b len[b], C], utterance b at row offset[b] = sum_{b' < b} len[b'] (offset[B] = the total).  Nearly
+// half of the padded [B, T3, 192] encoder input of a ragged batch is collate padding that no consumer reads; a D2H copy of
+// the packed rows halves the bytes on the host link.  One CTA per (utterance, 64-row slab); the offset is a block-wide sum.
+namespace {
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ len, int B, int T, int C,
+                                                        float* __restrict__ packed, int64_t* __restrict__ offset) {
+  __shared__ long long part[8];
+  __shared__ long long base_s;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  long long s = 0;
+  for (int i = tid; i < b; i += 256) s += max(0, min(len[i], T));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((tid & 31) == 0) part[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    long long t = 0;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    base_s = t;
+    if (blockIdx.x == 0) {
+      offset[b] = t;
+      if (b == B - 1) offset[B] = t + max(0, min(len[b], T));
+    }
+  }
+  __syncthreads();
+  const int L = max(0, min(len[b], T));
+  const int r0 = blockIdx.x * 64, r1 = min(L, r0 + 64);
+  if (r0 >= L) return;
+  const int c4 = C >> 2;
+  const float4* src = reinterpret_cast<const float4*>(x + ((size_t)b * T + r0) * C);
+  float4* dst = reinterpret_cast<float4*>(packed + ((size_t)base_s + r0) * C);
+  const int n4 = (r1 - r0) * c4;
+  for (int i = tid; i < n4; i += 256) dst[i] = __ldg(src + i);
+}
+}  // namespace
+
+extern "C" int tasr_pack_valid_rows(const float* x, const int32_t* len, int32_t B, int32_t T, int32_t C, float* packed,
+                                    int64_t* offset, tasr_stream_t stream) {
+  if (!x || !len || !packed || !offset) return fail(TASR_ERR_BAD_ARG, "tasr_pack_valid_rows: null argument");
+  if (B < 0 || T < 0 || C < 1) return fail(TASR_ERR_BAD_ARG, "tasr_pack_valid_rows: bad shape");
+  if ((C & 3) || !aligned16(x) || !aligned16(packed))
+    return fail(TASR_ERR_MISALIGNED, "tasr_pack_valid_rows: C must be a multiple of 4 and x / packed 16-byte aligned");
+  if (B > 65535) return fail(TASR_ERR_UNSUPPORTED, "tasr_pack_valid_rows: batch > 65535");
+  if (B == 0) return TASR_OK;
+  dim3 grid((unsigned)(T > 0 ? (T + 63) / 64 : 1), (unsigned)B);
+  pack_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, len, B, T, C, packed, offset);
+  TASR_LAUNCH_CHECK("pack_rows_kernel");
+  return TASR_OK;
+}

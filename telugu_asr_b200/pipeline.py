@@ -35,19 +35,27 @@ __all__ = ["FrontEndPipeline", "Ticket"]
 class Ticket:
     """Result handle of one submitted batch; `wait()` blocks until its D2H has landed."""
 
-    def __init__(self, slot: int, done: torch.cuda.Event, out, mask, len3):
+    def __init__(self, slot: int, done: torch.cuda.Event, out, mask, len3, offsets=None):
         self.slot, self.done = slot, done
-        self._out, self._mask, self._len3 = out, mask, len3
+        self._out, self._mask, self._len3, self._offsets = out, mask, len3, offsets
 
     def wait(self):
+        """(encoder_input [B, T3, d], padding_mask [B, max(len3)], len3 [B]) in pinned host memory; with the pipeline's
+        `packed_output=True`: (rows [sum(len3), d], offsets [B + 1] int64, len3 [B]) - utterance b is rows[offsets[b]:offsets[b+1]]."""
         self.done.synchronize()
+        if self._offsets is not None:
+            return self._out, self._offsets, self._len3
         return self._out, self._mask, self._len3
 
 
 class FrontEndPipeline:
     def __init__(self, frontend: FrontEnd, batch: int, n_max: int, device, pcm16: bool = True, slots: int = 2,
-                 graph: bool = True):
+                 graph: bool = True, packed_output: bool = False):
         self.fe = frontend
+        # packed_output: only the valid rows of the encoder input cross the host link on the way back ([sum(len3), d] +
+        # offsets instead of the zero-padded [B, T3, d] + mask: about half the D2H bytes of a ragged batch).  The row count
+        # of a batch is known on the host (integer arithmetic on the staged lengths), so the copy is sized without a sync.
+        self.packed_output = bool(packed_output)
         self.device = torch.device(device)
         self.batch, self.pcm16, self.slots = batch, pcm16, slots
         self.n_max = int(n_max)
@@ -105,19 +113,28 @@ class FrontEndPipeline:
                     hb = (torch.empty(out.shape, dtype=out.dtype).pin_memory(),
                           torch.empty(mask.shape, dtype=mask.dtype).pin_memory(),
                           torch.empty(len3.shape, dtype=len3.dtype).pin_memory())
+                    dev_rows = dev_offs = None
+                    if self.packed_output:
+                        dev_rows = torch.empty((out.shape[0] * out.shape[1], out.shape[2]), dtype=out.dtype, device=self.device)
+                        dev_offs = torch.empty((out.shape[0] + 1,), dtype=torch.int64, device=self.device)
                 st.synchronize()
                 l0 = _native.lib().tasr_launch_count()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=st):
                     wav, lens = pb.unpack()
                     out, mask, len3 = self.fe(wav, lens, max_length=self.n_max)
-                    hb[0].copy_(out, non_blocking=True)
-                    hb[1].copy_(mask, non_blocking=True)
+                    if self.packed_output:      # compaction inside the graph; the (batch-sized) D2H follows the replay
+                        _native.check(_native.lib().tasr_pack_valid_rows(out.data_ptr(), len3.data_ptr(), out.shape[0], out.shape[1],
+                                                                         out.shape[2], dev_rows.data_ptr(), dev_offs.data_ptr(),
+                                                                         _native.stream_ptr()))
+                    else:
+                        hb[0].copy_(out, non_blocking=True)
+                        hb[1].copy_(mask, non_blocking=True)
                     hb[2].copy_(len3, non_blocking=True)
                 self.kernels_per_submit = int(_native.lib().tasr_launch_count() - l0)
             finally:
                 pb.max_len = saved_max
-        self._graphs[slot] = (g, hb, tuple(self.fe.subsampling._plans or ()), (out, mask, len3))
+        self._graphs[slot] = (g, hb, tuple(self.fe.subsampling._plans or ()), (out, mask, len3, dev_rows, dev_offs))
         self.d2h_bytes = (hb[0].numel() + hb[1].numel()) * 4 + hb[2].numel() * 4
 
     def _views(self, slot: int, max_len: int):
@@ -152,9 +169,39 @@ class FrontEndPipeline:
             with torch.cuda.stream(st):
                 g.replay()
                 self.ev_free[slot].record(st)
+                if self.packed_output:
+                    len3_h = self._host_len3(pb.host_len.numpy())
+                    offs = torch.zeros((len(len3_h) + 1,), dtype=torch.int64)
+                    offs[1:] = torch.from_numpy(len3_h.clip(0, hb[0].shape[1]).astype("int64")).cumsum(0)
+                    rows = int(offs[-1])
+                    h_rows = hb[0].view(-1, hb[0].shape[-1])[:rows]
+                    h_rows.copy_(_keep[3][:rows], non_blocking=True)
+                    self.d2h_bytes = rows * hb[0].shape[-1] * 4 + hb[2].numel() * 4
                 self.ev_done[slot].record(st)
         self._used[slot] = True
+        if self.packed_output:
+            return Ticket(slot, self.ev_done[slot], h_rows, None, hb[2], offsets=offs)
         return Ticket(slot, self.ev_done[slot], *self._views(slot, pb.max_len))
+
+    def _host_len3(self, lengths):
+        """len3 of every utterance from its sample count, on the host, with the reference's arithmetic
+        (get_nframes, then get_conv_length per layer: float32, truncating cast) - the values the device computes."""
+        import numpy as np
+        sub, fz = self.fe.subsampling, self.fe.featurizer
+        n = np.asarray(lengths, dtype=np.int64)
+        if fz.pad_end:
+            t = -(-n // fz.frame_step)
+        else:
+            t = 1 + (n - fz.frame_length) // fz.frame_step
+        cur = np.maximum(t, 0).astype(np.int32)
+        for k, p, s_ in zip(sub.kernel_size, sub.padding, sub.strides):   # src/utils/math_util.py:20-32, vectorised
+            f = cur.astype(np.float32)
+            if p == "same":
+                f = np.ceil(f / np.float32(s_))
+            else:
+                f = (f - np.float32(k)) / np.float32(s_) + np.float32(1.0)
+            cur = np.trunc(f).astype(np.int32)
+        return cur
 
     def drain(self) -> None:
         """Block until everything submitted so far has landed in host memory."""

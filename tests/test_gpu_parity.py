@@ -1324,3 +1324,31 @@ def test_front_end_call_without_max_length_only_enqueues(cuda_device):
     assert m2.shape[1] == int(l2.max()) == want[1].shape[1] and torch.equal(m2, want[1]) and torch.equal(l2, want[2])
     L3 = int(l2.max())
     assert torch.equal(o2[:, :L3], want[0][:, :L3])
+
+
+def test_pipeline_packed_output_returns_only_valid_rows(cuda_device):
+    """FrontEndPipeline(packed_output=True): [sum(len3), d] + offsets instead of the zero-padded tensor; the rows are bit-identical
+    to the valid rows of the padded result, the offsets are the host-side prefix sums of len3 (incl. utterances shorter than a
+    frame), and fewer bytes cross the link."""
+    lens = [48000, 30000, 399, 16000, 5000, 0, 47999, 1250]
+    wav, ln = oracle.make_waveforms(lens, seed=9, dist="tilt")
+    utts = [wav[b, :L] for b, L in enumerate(lens)]
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    res = {}
+    for packed in (False, True):
+        fe = tasr.FrontEnd(math="tf32")
+        fe.set_weights(weights, cuda_device)
+        pipe = tasr.FrontEndPipeline(fe, batch=len(lens), n_max=48000, device=cuda_device, pcm16=True, packed_output=packed)
+        for _ in range(3):                               # slot reuse
+            pipe.stage(0, utts)
+            a, b, c = pipe.submit(0).wait()
+        res[packed] = (a.clone(), b.clone(), c.clone(), pipe.d2h_bytes)
+    out, mask, len3, bytes_padded = res[False]
+    rows, offs, len3p, bytes_packed = res[True]
+    assert torch.equal(len3, len3p)
+    L = len3.clamp(min=0).numpy()
+    assert offs.tolist() == [0] + np.cumsum(L).tolist()
+    assert rows.shape == (int(L.sum()), 192)
+    for b in range(len(lens)):
+        assert torch.equal(rows[offs[b]: offs[b + 1]], out[b, : L[b]])
+    assert bytes_packed < 0.7 * bytes_padded
