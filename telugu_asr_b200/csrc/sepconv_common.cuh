@@ -217,6 +217,65 @@ __device__ __forceinline__ void act_apply2(float acc0, float acc1, float b0, flo
   }
 }
 
+// bias add + activation of sixteen accumulator columns held as eight FP32x2 pairs, IN PLACE and STAGE BY STAGE: every stage is
+// applied to all eight pairs before the next one starts, so the sixteen MUFU / FMA dependency chains are in flight together.
+// (Written value by value — act_apply2 in a loop — ptxas reuses the same four registers for every group of four columns and the
+// chains run one after another: LDS -> FADD2 -> FMUL2 -> MUFU -> FADD2 -> MUFU -> FFMA2 -> STS, ~150 cycles each, 8 per block of 32
+// columns; that serial chain, not issue slots or the MUFU pipe, was what an epilogue warp spent its time on.)  Same operations in
+// the same order per value as act_apply2: identical bits.
+template <int ACT>
+__device__ __forceinline__ void act_block16(u64 (&z)[8]) {
+  if (ACT == TASR_ACT_TANH) {
+    float e[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) unpack2(mul2(z[i], pack2(2.88539008177792681472f, 2.88539008177792681472f)), e[2 * i], e[2 * i + 1]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) e[j] = ex2_approx(e[j]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) unpack2(add2(pack2(1.0f, 1.0f), pack2(e[2 * i], e[2 * i + 1])), e[2 * i], e[2 * i + 1]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) e[j] = rcp_approx(e[j]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = fma2(pack2(-2.0f, -2.0f), pack2(e[2 * i], e[2 * i + 1]), pack2(1.0f, 1.0f));
+  } else if (ACT == TASR_ACT_GELU_ERF) {
+    u64 a2[8], q[8];
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      unpack2(z[i], x[2 * i], x[2 * i + 1]);
+      a2[i] = pack2(fabsf(x[2 * i]), fabsf(x[2 * i + 1]));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = fma2(pack2(-4.732913936e-04f, -4.732913936e-04f), a2[i], pack2(7.084427742e-03f, 7.084427742e-03f));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = fma2(q[i], a2[i], pack2(-5.182704213e-02f, -5.182704213e-02f));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = fma2(q[i], a2[i], pack2(-4.599928375e-01f, -4.599928375e-01f));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = fma2(q[i], a2[i], pack2(-1.150787652e+00f, -1.150787652e+00f));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = fma2(q[i], a2[i], pack2(-3.765495672e-05f, -3.765495672e-05f));
+    float e[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) unpack2(q[i], e[2 * i], e[2 * i + 1]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) e[j] = ex2_approx(e[j]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t0, t1;
+      unpack2(mul2(mul2(pack2(0.5f, 0.5f), z[i]), pack2(e[2 * i], e[2 * i + 1])), t0, t1);
+      z[i] = pack2(fmaxf(x[2 * i], 0.0f) - fabsf(t0), fmaxf(x[2 * i + 1], 0.0f) - fabsf(t1));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float z0, z1;
+      unpack2(z[i], z0, z1);
+      z[i] = pack2(act_apply<ACT>(z0), act_apply<ACT>(z1));
+    }
+  }
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_apply(float z) {
   if (ACT == TASR_ACT_TANH) return tanh_fast(z);
