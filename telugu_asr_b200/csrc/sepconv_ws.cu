@@ -115,7 +115,7 @@ __host__ __device__ inline WsLayout ws_layout(int NT, int C_out) {
 }
 
 struct WsArgs {
-  CUtensorMap tm_hi;   // x as (C_in, T_in, B) float32, box 32 channels x 256 rows
+  CUtensorMap tm_hi;   // x as (C_in, T_in, B) float32, box 32 channels x 64 rows (up to four per window)
   CUtensorMap tm_lo;   // same tensor, box 32 channels x 8 rows (rows 256..263 of a tile's window)
   CUtensorMap tm_y;    // y as (C_out, T_out, B) float32, box 16 channels x 32 rows, SWIZZLE_64B: the epilogue's TMA stores
   SepArgs s;
@@ -438,14 +438,20 @@ __global__ void __launch_bounds__(ws_threads(DWG, EPW), 1) sepconv_ws_kernel(con
         for (int k = 0; k < n_c; ++k) {
           const int item = list_c[k];
           const int b = item >> 16, row0 = 2 * ((item >> 4) & 0xfff) * kMT + a.row_off;   // (negative / past-the-end rows arrive as zeros)
+          const int cf = utt_cf[b];
+          const int need = (cf >= 0x7fffff00) ? kXRows : min(kXRows, cf + 8 - row0);   // >= 9: the tile has a needed output
+          const int n64 = min(4, (need + 63) >> 6);
+          const bool tail = need > 256;
           for (int kc = 0; kc < n_chunks; ++kc, ++g) {
             const int s = g % kStagesX, n = g / kStagesX;
             if (n > 0) mbar_wait(bar_xempty(s), (n - 1) & 1);
             WS_TRACE(1, 800 + kc);
-            mbar_expect_tx(bar_xfull(s, n), (uint32_t)kXBytes);
+            // Only the rows a needed output can read are fetched: [row0, cf + 8) in 64-row boxes (+ the 8-row tail box).  The
+            // rest of the stage keeps stale values that only reach frames in the collate padding (replaced by the epilogue).
+            mbar_expect_tx(bar_xfull(s, n), (uint32_t)(n64 * 64 + (tail ? 8 : 0)) * kKC * 4u);
             const uint32_t dst = sX_u + (uint32_t)s * kXBytes;
-            tma_load_3d(dst, &wa.tm_hi, kc * kKC, row0, b, bar_xfull(s, n));
-            tma_load_3d(dst + 256u * kKC * 4u, &wa.tm_lo, kc * kKC, row0 + 256, b, bar_xfull(s, n));
+            for (int i = 0; i < n64; ++i) tma_load_3d(dst + (uint32_t)i * 64u * kKC * 4u, &wa.tm_hi, kc * kKC, row0 + 64 * i, b, bar_xfull(s, n));
+            if (tail) tma_load_3d(dst + 256u * kKC * 4u, &wa.tm_lo, kc * kKC, row0 + 256, b, bar_xfull(s, n));
           }
         }
       }
@@ -610,7 +616,7 @@ int tasr_sepconv_ws_launch(const TasrSepConvPlan* p, const SepArgs& sa_all, int3
     const cuuint64_t dims[3] = {(cuuint64_t)p->L.c_in, (cuuint64_t)sa.T_in, (cuuint64_t)B};
     const cuuint64_t strides[2] = {(cuuint64_t)p->L.c_in * 4, (cuuint64_t)sa.T_in * p->L.c_in * 4};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const cuuint32_t box_hi[3] = {(cuuint32_t)kKC, 256, 1}, box_lo[3] = {(cuuint32_t)kKC, 8, 1};
+    const cuuint32_t box_hi[3] = {(cuuint32_t)kKC, 64, 1}, box_lo[3] = {(cuuint32_t)kKC, 8, 1};
     CUresult r1 = encode(&wa.tm_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(sa.x), dims, strides, box_hi, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
