@@ -37,6 +37,7 @@ struct TasrConv2dPlan {
   // input width pat_w: [W2][F] floats, computed by these very kernels on a zero input (tasr_conv2d_plan_prepare_ragged)
   float* d_pattern;
   int pat_w;
+  float* d_scales;      // [s_h, s_w, 1 / (s_h * s_w)]: power-of-two FP16 range guard (conv2d_scales_kernel)
 };
 
 namespace {
@@ -45,6 +46,7 @@ struct C2Args {
   const __half* h1;
   const float* bpack;
   const float* bias;
+  const float* scales;   // [s_h, s_w, 1 / (s_h * s_w)] (conv2d_scales_kernel)
   float* y;
   int32_t H1, W1, H2, W2, F, NT, cpt, pt, pl;
   // ragged mode (n_frames != nullptr): feature rows t >= n_frames[b] are zero.  Output rows whose receptive field lies
@@ -132,8 +134,10 @@ __global__ void __launch_bounds__(MAXT, MINB) conv2d_first_kernel(const float* _
       // 9-tap sum of log-mel features — are far inside its range) HERE: h1 is only ever read as the A operand of the
       // tensor-core GEMM, so the second kernel moves its rows into the operand tiles with plain asynchronous copies,
       // and the big tensor costs half the bytes.
-      const __half2 lo = __floats2half2_rn(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f));
-      const __half2 hi = __floats2half2_rn(fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+      // The conversion SATURATES at the largest finite FP16 (no +inf / NaN can enter the GEMM); the plan scales the taps and the
+      // bias by a power of two so that this only happens for inputs far outside the feature range (conv2d_scales_kernel).
+      const __half2 lo = __floats2half2_rn(fminf(fmaxf(acc.x, 0.f), 65504.f), fminf(fmaxf(acc.y, 0.f), 65504.f));
+      const __half2 hi = __floats2half2_rn(fminf(fmaxf(acc.z, 0.f), 65504.f), fminf(fmaxf(acc.w, 0.f), 65504.f));
       uint2 pk;
       pk.x = *reinterpret_cast<const uint32_t*>(&lo);
       pk.y = *reinterpret_cast<const uint32_t*>(&hi);
@@ -294,6 +298,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv2d_f16_kernel(const C2Args a)
     const int q = warp & 3, half = warp >> 2;
     float* stg = reinterpret_cast<float*>(sm) + warp * (32 * kStgStride);   // aliases A/B (all MMAs done, no copy in flight)
     const int ngroups = NT >> 5;
+    const float unscale = __ldg(a.scales + 2);   // 1 / (s_h * s_w): an exact power of two (conv2d_scales_kernel)
     for (int g = half; g < ngroups; g += 2) {
       uint32_t r[32];
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32), r);
@@ -302,10 +307,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv2d_f16_kernel(const C2Args a)
       for (int i = 0; i < 8; ++i) {
         const float4 bv = *reinterpret_cast<const float4*>(sBias + g * 32 + 4 * i);
         float4 o;
-        o.x = fmaxf(__uint_as_float(r[4 * i + 0]) + bv.x, 0.0f);
-        o.y = fmaxf(__uint_as_float(r[4 * i + 1]) + bv.y, 0.0f);
-        o.z = fmaxf(__uint_as_float(r[4 * i + 2]) + bv.z, 0.0f);
-        o.w = fmaxf(__uint_as_float(r[4 * i + 3]) + bv.w, 0.0f);
+        o.x = fmaxf(fmaf(__uint_as_float(r[4 * i + 0]), unscale, bv.x), 0.0f);
+        o.y = fmaxf(fmaf(__uint_as_float(r[4 * i + 1]), unscale, bv.y), 0.0f);
+        o.z = fmaxf(fmaf(__uint_as_float(r[4 * i + 2]), unscale, bv.z), 0.0f);
+        o.w = fmaxf(fmaf(__uint_as_float(r[4 * i + 3]), unscale, bv.w), 0.0f);
         *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * i) = o;
       }
       __syncwarp();
@@ -331,7 +336,55 @@ __global__ void __launch_bounds__(kThreads, 2) conv2d_f16_kernel(const C2Args a)
 // w2 [3,3,F,F] (Keras kernel: tap, c_in, c_out) -> per (tap, chunk) shared-memory image of B: row n (128 bytes) holds
 // input channels c0..c0+63 of filter n as FP16, 16-byte groups (8 channels) XOR-swizzled by (n & 7); rows n >= F and
 // channels >= F are zero.  `out` is addressed in halves; one chunk image is NT*64 halves = NT*128 bytes.
-__global__ void pack_w2_kernel(const float* __restrict__ w2, int F, int NT, int cpt, __half* __restrict__ out) {
+// FP16 range guard.  The tensor-core GEMM reads h1 = ReLU(conv1) and w2 as FP16 (11 significant bits like TF32, but only 5
+// exponent bits), so the plan rescales both by exact powers of two, decided on the device from the weights it is given:
+//   s_w = 2^-e with max|w2| = f * 2^e, f in [0.5, 1): the packed weights lie in (-1, 1), the largest in [0.5, 1) — no overflow
+//         for large trained weights and no FP16 subnormals until 2^-14 of the largest weight;
+//   s_h = the largest power of two <= 1 with  max_f (16 * sum_taps |w1[.,f]| + |b1[f]|) * s_h <= 32768: features up to 16 in
+//         magnitude (log-mel lies in [-9, 5], z-scored features within a few units) cannot reach the FP16 maximum; anything
+//         beyond saturates at 65504 in conv1's store instead of turning into +inf.
+// conv1 runs on s_h * (w1, b1), the GEMM accumulates s_h * s_w * (the sum), the epilogue multiplies by 1 / (s_h * s_w) before the
+// bias: all three factors are powers of two, so for weights inside the FP16 range every result bit is what it was without them.
+__global__ void conv2d_scales_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                                     int F, float* __restrict__ scales, float* __restrict__ w1s, float* __restrict__ b1s) {
+  __shared__ float red[2][32];
+  float m2 = 0.0f, bnd = 0.0f;
+  for (size_t i = threadIdx.x; i < (size_t)9 * F * F; i += blockDim.x) m2 = fmaxf(m2, fabsf(w2[i]));
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float sum = 0.0f;
+    for (int k = 0; k < 9; ++k) sum += fabsf(w1[k * F + f]);
+    bnd = fmaxf(bnd, 16.0f * sum + fabsf(b1[f]));
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, d));
+    bnd = fmaxf(bnd, __shfl_xor_sync(0xffffffffu, bnd, d));
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = m2; red[1][threadIdx.x >> 5] = bnd; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m2 = threadIdx.x < (blockDim.x >> 5) ? red[0][threadIdx.x] : 0.0f;
+    bnd = threadIdx.x < (blockDim.x >> 5) ? red[1][threadIdx.x] : 0.0f;
+    for (int d = 16; d > 0; d >>= 1) {
+      m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, d));
+      bnd = fmaxf(bnd, __shfl_xor_sync(0xffffffffu, bnd, d));
+    }
+    if (threadIdx.x == 0) {
+      float s_w = 1.0f, s_h = 1.0f;
+      int e;
+      if (m2 > 0.0f && m2 < 3.0e38f) { frexpf(m2, &e); s_w = ldexpf(1.0f, max(-60, min(60, -e))); }
+      if (bnd > 32768.0f && bnd < 3.0e38f) { frexpf(bnd / 32768.0f, &e); s_h = ldexpf(1.0f, max(-60, -e)); }
+      red[0][0] = s_h;
+      scales[0] = s_h; scales[1] = s_w; scales[2] = 1.0f / (s_h * s_w);
+    }
+  }
+  __syncthreads();
+  const float s_h = red[0][0];
+  for (int i = threadIdx.x; i < 9 * F; i += blockDim.x) w1s[i] = w1[i] * s_h;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) b1s[i] = b1[i] * s_h;
+}
+
+__global__ void pack_w2_kernel(const float* __restrict__ w2, int F, int NT, int cpt, const float* __restrict__ scales, __half* __restrict__ out) {
+  const float s_w = scales[1];
   const size_t total = (size_t)9 * cpt * NT * kC2KC;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int cl = (int)(i % kC2KC);
@@ -341,7 +394,7 @@ __global__ void pack_w2_kernel(const float* __restrict__ w2, int F, int NT, int 
     const float v = (c < F && n < F) ? w2[((size_t)tap * F + c) * F + n] : 0.0f;
     const size_t base = (size_t)kc * NT * kC2KC;
     const int phys = n * kC2KC + ((((cl >> 3) ^ (n & 7)) << 3) | (cl & 7));
-    out[base + phys] = __float2half_rn(v);
+    out[base + phys] = __float2half_rn(v * s_w);   // |v * s_w| < 1
   }
 }
 
@@ -366,7 +419,7 @@ extern "C" int tasr_conv2d_plan_create(const float* w1, const float* b1, const f
   p->filters = filters;
   p->NT = (filters + 31) & ~31;
   p->cpt = (filters + kC2KC - 1) / kC2KC;
-  p->d_w1 = p->d_b1 = p->d_b2 = p->d_bpack = nullptr;
+  p->d_w1 = p->d_b1 = p->d_b2 = p->d_bpack = p->d_scales = nullptr;
   p->d_pattern = nullptr;
   p->pat_w = 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -376,13 +429,17 @@ extern "C" int tasr_conv2d_plan_create(const float* w1, const float* b1, const f
   if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_b1, (size_t)filters * sizeof(float)), "cudaMalloc conv1 bias");
   if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_b2, (size_t)p->NT * sizeof(float)), "cudaMalloc conv2 bias");
   if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_bpack, nb * sizeof(float)), "cudaMalloc packed conv2 weights");
-  if (rc == TASR_OK) rc = check_cuda(cudaMemcpyAsync(p->d_w1, w1, (size_t)9 * filters * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy conv1 taps");
-  if (rc == TASR_OK) rc = check_cuda(cudaMemcpyAsync(p->d_b1, b1, (size_t)filters * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy conv1 bias");
+  if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_scales, 4 * sizeof(float)), "cudaMalloc conv2d scales");
+  if (rc == TASR_OK) {   // s_h, s_w and the scaled copies of the conv1 taps / bias (no host synchronisation: the weights are device pointers)
+    conv2d_scales_kernel<<<1, 1024, 0, st>>>(w1, b1, w2, filters, p->d_scales, p->d_w1, p->d_b1);
+    count_launch();
+    rc = check_cuda(cudaGetLastError(), "conv2d_scales_kernel");
+  }
   if (rc == TASR_OK) rc = check_cuda(cudaMemsetAsync(p->d_b2, 0, (size_t)p->NT * sizeof(float), st), "clear conv2 bias");
   if (rc == TASR_OK) rc = check_cuda(cudaMemcpyAsync(p->d_b2, b2, (size_t)filters * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy conv2 bias");
   if (rc == TASR_OK) {
     pack_w2_kernel<<<(unsigned)((2 * nb + 255) / 256 > 1024 ? 1024 : (2 * nb + 255) / 256), 256, 0, st>>>(
-        w2, filters, p->NT, p->cpt, reinterpret_cast<__half*>(p->d_bpack));
+        w2, filters, p->NT, p->cpt, p->d_scales, reinterpret_cast<__half*>(p->d_bpack));
     count_launch();
     rc = check_cuda(cudaGetLastError(), "pack_w2_kernel");
   }
@@ -396,7 +453,7 @@ extern "C" int tasr_conv2d_plan_create(const float* w1, const float* b1, const f
 
 extern "C" int tasr_conv2d_plan_destroy(TasrConv2dPlan* p) {
   if (!p) return TASR_OK;
-  cudaFree(p->d_w1); cudaFree(p->d_b1); cudaFree(p->d_b2); cudaFree(p->d_bpack); cudaFree(p->d_pattern);
+  cudaFree(p->d_w1); cudaFree(p->d_b1); cudaFree(p->d_b2); cudaFree(p->d_bpack); cudaFree(p->d_pattern); cudaFree(p->d_scales);
   delete p;
   return TASR_OK;
 }
@@ -442,7 +499,7 @@ static int conv2d_launch(const char* who, const TasrConv2dPlan* p, const float* 
     TASR_LAUNCH_CHECK("conv2d_first_kernel");
   }
   C2Args a;
-  a.h1 = reinterpret_cast<const __half*>(h1); a.bpack = p->d_bpack; a.bias = p->d_b2; a.y = out;
+  a.h1 = reinterpret_cast<const __half*>(h1); a.bpack = p->d_bpack; a.bias = p->d_b2; a.scales = p->d_scales; a.y = out;
   a.H1 = H1; a.W1 = W1; a.H2 = H2; a.W2 = W2; a.F = F; a.NT = p->NT; a.cpt = p->cpt; a.pt = pt2; a.pl = pl2;
   a.n_frames = n_frames; a.pattern = p->d_pattern; a.pt1 = pt1;
   const int M_total = H2 * W2;

@@ -942,6 +942,46 @@ def test_conv2d_subsampling_matches_oracle(cuda_device, T, B, filters):
         layer.set_weights([(ws[0][0][:2], ws[0][1]), ws[1]], cuda_device)
 
 
+@pytest.mark.parametrize("scale1,scale2", [(1.0, 1.0), (3000.0, 1.0), (1.0, 1e-6), (2.0e4, 4.0e5), (1e-3, 1e-7)])
+def test_conv2d_subsampling_fp16_range_guard(cuda_device, scale1, scale2):
+    """The second convolution reads ReLU(conv1) and its weights as FP16 (csrc/conv2d_subsample.cu): trained weights far from
+    unit scale must neither overflow (conv1 outputs of 1e5 and more with scale1 = 3000 / 2e4, second-layer weights of 1e4 with
+    scale2 = 4e5) nor sink into FP16 subnormals (weights of 5e-8 with scale2 = 1e-6 / 1e-7).  The plan's power-of-two scales
+    (conv2d_scales_kernel) keep both operands inside the FP16 range: same relative accuracy as at unit scale, no inf / NaN."""
+    T, B, filters = 203, 3, 144
+    rng = np.random.default_rng(77)
+    x = (rng.standard_normal((B, T, 80, 1)) * 3.0 - 2.0).astype(np.float32)          # log-mel like: roughly [-11, 7]
+    lens = np.array([T, T // 2, 9], dtype=np.int32)
+    for b in range(B):
+        x[b, lens[b]:] = 0.0
+    ws = oracle.glorot_conv2d_weights(filters, seed=11)
+    ws = [(ws[0][0] * np.float32(scale1), ws[0][1] * np.float32(scale1)), (ws[1][0] * np.float32(scale2), ws[1][1] * np.float32(scale1 * scale2))]
+    layer = tasr.Conv2dSubsampling({"name": "conv2d", "filters": filters, "kernel_size": 3, "strides": 2, "padding": "same"})
+    layer.set_weights(ws, cuda_device)
+    out, _ = _call_or_skip(layer, [gpu(x, cuda_device), gpu(lens, cuda_device)])
+    torch.cuda.synchronize()
+    ref, _ = oracle.conv2d_subsample_ref(x, lens, ws, dtype=np.float64)
+    o = out.cpu().numpy()
+    assert np.isfinite(o).all()
+    rel = np.abs(o - ref).max() / np.abs(ref).max()
+    assert rel <= SUB_TOL_TF32, (scale1, scale2, rel)
+
+
+def test_conv2d_subsampling_saturates_instead_of_overflowing(cuda_device):
+    """Features far outside the range the plan's scale assumes (|x| <= 16): conv1's FP16 store saturates at 65504, so the output
+    stays finite (the reference would return the un-saturated float32 value; no inf or NaN is produced here)."""
+    T, B, filters = 64, 1, 144
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((B, T, 80, 1)) * 1.0e6).astype(np.float32)
+    lens = np.array([T], dtype=np.int32)
+    ws = oracle.glorot_conv2d_weights(filters, seed=3)
+    layer = tasr.Conv2dSubsampling({"name": "conv2d", "filters": filters, "kernel_size": 3, "strides": 2, "padding": "same"})
+    layer.set_weights(ws, cuda_device)
+    out, _ = _call_or_skip(layer, [gpu(x, cuda_device), gpu(lens, cuda_device)])
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+
+
 @pytest.mark.parametrize("T", [1498, 1497, 203])
 def test_conv2d_subsampling_ragged_is_bit_identical_to_dense(cuda_device, T):
     """Ragged mode fills the tiles that lie in the collate padding with the pattern the two convolutions produce
