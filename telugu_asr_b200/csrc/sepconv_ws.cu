@@ -379,32 +379,44 @@ __global__ void __launch_bounds__(ws_threads(DWG, EPW), 1) sepconv_ws_kernel(con
       mbar_wait(bar_accf(acc), (k >> 1) & 1);
       tc_fence_after();
       if (e == 0 || e == EPW - 1) WS_TRACE(e == 0 ? 3 : 4, 301);
-      for (int g = slice; g < nblocks; g += kSlices) {
-        uint32_t r[16];
-        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + g * 16), r);
-        u64 z[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 bv = *reinterpret_cast<const float4*>(sBias + n0 + g * 16 + 4 * i);
-          z[2 * i] = add2(pack2(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1])), pack2(bv.x, bv.y));
-          z[2 * i + 1] = add2(pack2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), pack2(bv.z, bv.w));
-        }
-        act_block16<ACT>(z);
-        // the staging tile this block goes to was last read by the store issued kTiles blocks ago
-        if (lane == 0 && issued >= kTiles) bulk_wait_read<kTiles - 1>();
+      for (int g0 = slice; g0 < nblocks; g0 += kSlices * kTiles) {
+        // kTiles column blocks per round (one per staging tile): one proxy fence and one hand-off to lane 0 for all of them
+        if (lane == 0 && issued > 0) bulk_wait_read<0>();   // the previous round's stores have read the staging tiles
         __syncwarp();
-        unsigned char* tile = stg + (kTiles == 2 ? (issued & 1) * kStgTile : 0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4 o;
-          unpack2(z[2 * i], o.x, o.y);
-          unpack2(z[2 * i + 1], o.z, o.w);
-          if (is_pad) o = __ldg(reinterpret_cast<const float4*>(a.pad_out + n0 + g * 16 + 4 * i));
-          *reinterpret_cast<float4*>(tile + lane * 64 + (((uint32_t)i ^ (((uint32_t)lane >> 1) & 3u)) << 4)) = o;
+        for (int j = 0; j < kTiles; ++j) {
+          const int g = g0 + j * kSlices;
+          if (g < nblocks) {
+            uint32_t r[16];
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + g * 16), r);
+            u64 z[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 bv = *reinterpret_cast<const float4*>(sBias + n0 + g * 16 + 4 * i);
+              z[2 * i] = add2(pack2(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1])), pack2(bv.x, bv.y));
+              z[2 * i + 1] = add2(pack2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), pack2(bv.z, bv.w));
+            }
+            act_block16<ACT>(z);
+            unsigned char* tile = stg + j * kStgTile;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float4 o;
+              unpack2(z[2 * i], o.x, o.y);
+              unpack2(z[2 * i + 1], o.z, o.w);
+              if (is_pad) o = __ldg(reinterpret_cast<const float4*>(a.pad_out + n0 + g * 16 + 4 * i));
+              *reinterpret_cast<float4*>(tile + lane * 64 + (((uint32_t)i ^ (((uint32_t)lane >> 1) & 3u)) << 4)) = o;
+            }
+          }
         }
         fence_async_smem();                  // generic-proxy writes -> visible to the TMA engine (async proxy)
         __syncwarp();
-        if (lane == 0) tma_store_3d(&wa.tm_y, n0 + g * 16, t0 + q * 32, b, stg_u + (kTiles == 2 ? (issued & 1) * kStgTile : 0));
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < kTiles; ++j) {
+            const int g = g0 + j * kSlices;
+            if (g < nblocks) tma_store_3d(&wa.tm_y, n0 + g * 16, t0 + q * 32, b, stg_u + j * kStgTile);
+          }
+        }
         ++issued;
       }
       tc_fence_before();
