@@ -16,6 +16,8 @@ struct TasrSepConvPlan {
   float* d_pad_out;     // [c_out]    this layer's output for an all-padding receptive field
   int pad_ready;
   int use_ws;           // 1: persistent warp-specialised kernel (sepconv_ws.cu) when the shape allows it
+  int ws_roles;         // role counts of the persistent kernel: 28 (two depthwise groups, 8 epilogue warps; default), 18, 116;
+                        // TASR_WS_ROLES at plan creation (development aid, all bit-identical)
 };
 
 namespace tasr_sep {

@@ -310,6 +310,9 @@ extern "C" int tasr_sepconv_plan_create(const TasrSepConvLayer* L, TasrSepConvPl
      // to the per-tile kernel by themselves.  TASR_SEPCONV_WS=0 / 1: never / always try it.
     const char* e = getenv("TASR_SEPCONV_WS");
     p->use_ws = e ? (e[0] == '1' ? 1 : 0) : 1;
+    const char* r = getenv("TASR_WS_ROLES");
+    const int roles = r ? atoi(r) : 0;
+    p->ws_roles = (roles == 18 || roles == 116) ? roles : 28;
   }
   int rc = check_cuda(cudaGetDevice(&p->device), "cudaGetDevice");
   if (rc == TASR_OK) rc = check_cuda(cudaMalloc(&p->d_pad_in, (size_t)9 * L->c_in * sizeof(float)), "cudaMalloc pad rows");

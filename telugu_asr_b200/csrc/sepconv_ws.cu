@@ -607,9 +607,8 @@ int tasr_sepconv_ws_launch(const TasrSepConvPlan* p, const SepArgs& sa_all, int3
   const size_t smem = (size_t)L.total + 1024;
   if (smem > 227 * 1024) return -1;
   // Role counts: two depthwise groups on alternate chunks wherever that instantiation exists (layers 2 / 3 are bound by the
-  // depthwise chain; layer 1 is not slower with it); TASR_WS_ROLES = 18 | 28 | 116 overrides (development aid).
-  static const int roles_env = [] { const char* e = getenv("TASR_WS_ROLES"); return e ? atoi(e) : 0; }();
-  int roles = roles_env ? roles_env : 28;
+  // depthwise chain; layer 1 is not slower with it); the plan's TASR_WS_ROLES = 18 | 28 | 116 overrides (development aid).
+  int roles = p->ws_roles;
   WsKernel kern = roles == 116 ? pick_kernel_ws<1, 16>(p->L.c_in, p->L.activation)
                 : roles == 28 ? pick_kernel_ws<2, 8>(p->L.c_in, p->L.activation) : nullptr;
   if (kern == nullptr) { roles = 18; kern = pick_kernel_ws<1, 8>(p->L.c_in, p->L.activation); }

@@ -1040,6 +1040,54 @@ def test_persistent_kernel_applies_the_deferred_gain_bitwise(cuda_device, monkey
     assert not torch.isnan(res["1"][0]).any()
 
 
+@pytest.mark.parametrize("roles", ["18", "116"])
+def test_persistent_kernel_role_counts_are_bit_identical(cuda_device, monkeypatch, roles):
+    """The persistent kernel's other role counts (one depthwise group; sixteen epilogue warps — TASR_WS_ROLES at plan creation) must
+    give the bits of the default (two depthwise groups, eight epilogue warps): same arithmetic, different schedule."""
+    from telugu_asr_b200.synth import draw_lengths
+    lens = draw_lengths(40, 1600, 240000, seed=21)
+    lens[0], lens[1] = 240000, 400
+    wav, ln = oracle.make_waveforms(lens, seed=21, dist="tilt")
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    w, l = gpu(wav, cuda_device), gpu(ln, cuda_device)
+    res = {}
+    for r in ("28", roles):
+        monkeypatch.setenv("TASR_WS_ROLES", r)
+        fe = tasr.FrontEnd(math="tf32")
+        fe.set_weights(weights, cuda_device)
+        res[r] = _call_or_skip(fe, w, l)
+        torch.cuda.synchronize()
+    for a, b in zip(res["28"], res[roles]):
+        assert torch.equal(a, b)
+
+
+def test_persistent_kernel_repeated_launches_are_stable(cuda_device):
+    """Forty replays of the three ragged layers on a config-3-like batch (full padding fill: the shape on which two depthwise
+    groups on a single x-full barrier per stage failed in 2 of 8 runs, out-of-order TMA completion): every replay must reproduce
+    the first one's bits, and no launch may fail."""
+    from telugu_asr_b200.synth import draw_lengths
+    B = 128
+    lens = draw_lengths(B, 16000, 240000, seed=33)
+    rng = np.random.default_rng(33)
+    T = 1498
+    nf = np.minimum((np.asarray(lens) - 400) // 160 + 1, T).astype(np.int32)
+    feat = rng.standard_normal((B, T, 80, 1)).astype(np.float32)
+    for b in range(B):
+        feat[b, nf[b]:] = 0.0
+    weights = oracle.glorot_subsampling_weights(192, 80, seed=7)
+    layer = tasr.Conv1DSubsamplingLayer(192, dict(tasr.REFERENCE_SUBSAMPLING_CONFIG), math="tf32")
+    layer.set_weights(weights, cuda_device)
+    x, n = gpu(feat, cuda_device), gpu(nf, cuda_device)
+    first = None
+    for _ in range(40):
+        out, mask = layer(x, mask=n)
+        torch.cuda.synchronize()
+        if first is None:
+            first = out.clone()
+        else:
+            assert torch.equal(out, first)
+
+
 def test_persistent_kernel_sub_batches_above_512_utterances(cuda_device, monkeypatch):
     """More than 512 utterances run through the persistent kernel as consecutive sub-batches: identical bits to the
     per-tile kernel, single-pass front end (deferred gain pointers are offset per sub-batch too)."""
