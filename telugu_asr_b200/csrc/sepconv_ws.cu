@@ -46,7 +46,8 @@ namespace {
 constexpr int kDwWarps = 8;                     // warps per depthwise group
 constexpr int kRunWs = kMT / kDwWarps;          // 16 output frames per depthwise warp
 constexpr int kWinWs = 2 * (kRunWs - 1) + 9;    // 39 input rows per run
-constexpr int kStagesA = 2;   // depthwise -> MMA ring (16 KB each); with two depthwise groups, group i owns stage i
+// depthwise -> MMA ring: STA stages of 16 KB (template parameter: 2, or 3 for the layers bound by the depthwise -> MMA -> commit
+// round trip, which then stage their epilogue tiles single-buffered: the 16 KB come from there)
 constexpr int kStagesB = 2;   // pw^T chunk ring (NT*128 B each)
 constexpr int kStagesX = 3;   // input-tile ring: 264 rows x 32 channels fetched by TMA two chunks ahead of the arithmetic
 constexpr int kXRows = 264;   // 2*(128-1)+9 = 263 rows per 128-frame tile, fetched as boxes of 256 + 8 rows
@@ -55,7 +56,7 @@ constexpr int kMaxUtt = 512;      // utterances indexed in shared memory
 constexpr int kListCap = 256;    // work items per CTA
 constexpr int kTmemColsWs = 512;
 constexpr int kStgTile = 32 * 64;       // one staging tile: 32 frames x 16 channels, the SWIZZLE_64B image a TMA store reads
-constexpr int kStgBytes = 16 * kStgTile;   // 8 epilogue warps x 2 tiles or 16 warps x 1 tile
+__host__ __device__ constexpr int ws_stg_bytes(int sta) { return (sta == 3 ? 8 : 16) * kStgTile; }   // 16 tiles (8 warps x 2 or 16 x 1), or 8 x 1
 __host__ __device__ constexpr int ws_threads(int dwg, int epw) { return (dwg * kDwWarps + epw + 4) * 32; }
 
 // TMA tiled load of a 3-D box (coordinates: channel, row, utterance) onto an mbarrier; out-of-range rows and
@@ -93,13 +94,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 struct WsLayout {
   uint32_t a, b, xs, stg, bias, cum_c, cum_f, utt_cf, utt_gc, list_c, list_f, bars, tmem_slot, total;
 };
-__host__ __device__ inline WsLayout ws_layout(int NT, int C_out) {
+__host__ __device__ inline WsLayout ws_layout(int NT, int C_out, int sta) {
   WsLayout L;
   uint32_t o = 0;
-  L.a = o; o += kStagesA * kABytes;
+  L.a = o; o += sta * kABytes;
   L.b = o; o += kStagesB * (uint32_t)NT * 128u;
   L.xs = o; o += kStagesX * kXBytes;
-  L.stg = o; o += kStgBytes;                 // (a, b and xs are multiples of 1024 bytes: the tiles are 2048-byte aligned)
+  L.stg = o; o += ws_stg_bytes(sta);         // (a, b and xs are multiples of 1024 bytes: the tiles are 2048-byte aligned)
   L.bias = o; o += (uint32_t)((C_out + 3) & ~3) * 4u;
   L.cum_c = o; o += (kMaxUtt + 1) * 4;
   L.cum_f = o; o += (kMaxUtt + 1) * 4;
@@ -137,8 +138,9 @@ __device__ __forceinline__ long long gtime() {
     }                                                                                  \
   } while (0)
 
-template <int CIN, int ACT, int DWG, int EPW>
+template <int CIN, int ACT, int DWG, int EPW, int STA>
 __global__ void __launch_bounds__(ws_threads(DWG, EPW), 1) sepconv_ws_kernel(const __grid_constant__ WsArgs wa) {
+  constexpr int kStagesA = STA;
   constexpr int kWsThreads = ws_threads(DWG, EPW);
   constexpr int kDwAll = DWG * kDwWarps;
   constexpr bool kRedeal = kWsThreads > 640;       // 896 threads start at 72 registers: re-dealt per role below
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(ws_threads(DWG, EPW), 1) sepconv_ws_kernel(con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NT = a.NT;
   const uint32_t bBytes = (uint32_t)NT * 128u;
-  const WsLayout L = ws_layout(NT, a.C_out);
+  const WsLayout L = ws_layout(NT, a.C_out, STA);
   const long long t_entry = (wa.trace != nullptr) ? gtime() : 0;
   constexpr int kWarpB = kDwAll + EPW, kWarpX = kWarpB + 1, kWarpMma = kWarpB + 2;   // kWarpB + 3: padding fill
   if (warp == kWarpX && lane == 0) {
@@ -361,7 +363,8 @@ __global__ void __launch_bounds__(ws_threads(DWG, EPW), 1) sepconv_ws_kernel(con
     // stores) -> one TMA tensor store of the 16 x 32 box by lane 0.  Frames beyond T_out are clipped by the tensor map,
     // frames in the collate padding take the layer's constant row.
     if (kRedeal && EPW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    constexpr int kTiles = 16 / EPW;          // staging tiles per warp: 2 (double-buffered) or 1
+    constexpr int kTiles = ws_stg_bytes(STA) / kStgTile / EPW;   // staging tiles per warp: 2 (double-buffered) or 1
+    static_assert(kTiles >= 1, "no staging tile for this role / stage combination");
     constexpr int kSlices = EPW / 4;          // warps per TMEM lane quadrant
     const int e = warp - kDwAll;
     const int q = e & 3, slice = e >> 2;      // TMEM lane quadrant (= warp id % 4), column-block phase
@@ -544,26 +547,26 @@ __global__ void __launch_bounds__(ws_threads(DWG, EPW), 1) sepconv_ws_kernel(con
 }
 
 typedef void (*WsKernel)(const WsArgs);
-template <int CIN, int DWG, int EPW>
+template <int CIN, int DWG, int EPW, int STA>
 WsKernel pick_act_ws(int act) {
   switch (act) {
-    case TASR_ACT_TANH: return sepconv_ws_kernel<CIN, TASR_ACT_TANH, DWG, EPW>;
-    case TASR_ACT_GELU_ERF: return sepconv_ws_kernel<CIN, TASR_ACT_GELU_ERF, DWG, EPW>;
+    case TASR_ACT_TANH: return sepconv_ws_kernel<CIN, TASR_ACT_TANH, DWG, EPW, STA>;
+    case TASR_ACT_GELU_ERF: return sepconv_ws_kernel<CIN, TASR_ACT_GELU_ERF, DWG, EPW, STA>;
     default: break;
   }
   if (DWG != 1 || EPW != 8) return nullptr;      // the other activations / widths only exist with the base role counts
   switch (act) {
-    case TASR_ACT_RELU: return sepconv_ws_kernel<CIN, TASR_ACT_RELU, 1, 8>;
-    default: return sepconv_ws_kernel<CIN, TASR_ACT_NONE, 1, 8>;
+    case TASR_ACT_RELU: return sepconv_ws_kernel<CIN, TASR_ACT_RELU, 1, 8, 2>;
+    default: return sepconv_ws_kernel<CIN, TASR_ACT_NONE, 1, 8, 2>;
   }
 }
-template <int DWG, int EPW>
+template <int DWG, int EPW, int STA>
 WsKernel pick_kernel_ws(int c_in, int act) {
   switch (c_in) {
-    case 80: return pick_act_ws<80, DWG, EPW>(act);
-    case 192: return pick_act_ws<192, DWG, EPW>(act);
-    case 384: return pick_act_ws<384, DWG, EPW>(act);
-    default: return (DWG == 1 && EPW == 8) ? pick_act_ws<0, 1, 8>(act) : nullptr;
+    case 80: return pick_act_ws<80, DWG, EPW, STA>(act);
+    case 192: return pick_act_ws<192, DWG, EPW, STA>(act);
+    case 384: return pick_act_ws<384, DWG, EPW, STA>(act);
+    default: return (DWG == 1 && EPW == 8) ? pick_act_ws<0, 1, 8, 2>(act) : nullptr;
   }
 }
 
@@ -603,16 +606,20 @@ int tasr_sepconv_ws_launch(const TasrSepConvPlan* p, const SepArgs& sa_all, int3
   const int grid = sm_count();
   const long long dense = (long long)B * n_tiles * p->n_split;
   if ((dense + grid - 1) / grid > kListCap) return -1;
-  const WsLayout L = ws_layout(p->NT, p->L.c_out);
+  // Role counts: two depthwise groups on alternate chunks wherever that instantiation exists (layers 2 / 3 are bound by the
+  // depthwise chain; layer 1 is not slower with it), with a third A stage for the layers of more than three chunks per tile
+  // (layer 1 is bound by its epilogue and keeps the double-buffered staging tiles instead); the plan's
+  // TASR_WS_ROLES = 18 | 28 | 116 overrides (development aid).
+  int roles = p->ws_roles;
+  const int sta = (roles == 28 && p->n_chunks > 3) ? 3 : 2;
+  WsKernel kern = roles == 116 ? pick_kernel_ws<1, 16, 2>(p->L.c_in, p->L.activation)
+                : roles == 28 ? (sta == 3 ? pick_kernel_ws<2, 8, 3>(p->L.c_in, p->L.activation) : pick_kernel_ws<2, 8, 2>(p->L.c_in, p->L.activation))
+                              : nullptr;
+  if (kern == nullptr) { roles = 18; kern = pick_kernel_ws<1, 8, 2>(p->L.c_in, p->L.activation); }
+  const int threads = roles == 18 ? ws_threads(1, 8) : ws_threads(2, 8);
+  const WsLayout L = ws_layout(p->NT, p->L.c_out, roles == 28 ? sta : 2);
   const size_t smem = (size_t)L.total + 1024;
   if (smem > 227 * 1024) return -1;
-  // Role counts: two depthwise groups on alternate chunks wherever that instantiation exists (layers 2 / 3 are bound by the
-  // depthwise chain; layer 1 is not slower with it); the plan's TASR_WS_ROLES = 18 | 28 | 116 overrides (development aid).
-  int roles = p->ws_roles;
-  WsKernel kern = roles == 116 ? pick_kernel_ws<1, 16>(p->L.c_in, p->L.activation)
-                : roles == 28 ? pick_kernel_ws<2, 8>(p->L.c_in, p->L.activation) : nullptr;
-  if (kern == nullptr) { roles = 18; kern = pick_kernel_ws<1, 8>(p->L.c_in, p->L.activation); }
-  const int threads = roles == 18 ? ws_threads(1, 8) : ws_threads(2, 8);
   TASR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   WsArgs wa;
   {
