@@ -29,10 +29,19 @@ rows = list(csv.DictReader(l for l in open(src) if l.startswith('"')))
 launches = [(short(r["Kernel Name"]), r["Grid Size"], r["Block Size"], float(r["Metric Value"]) / 1e3) for r in rows]
 # one step = from one launch of the step's first kernel to the next, taken in the middle of the run (graph replays / the eager stage
 # pass on the real batch; the first launches are plan set-up and the graph-capture warm-ups on empty buffers)
-first = "absmax_kernel" if any(l[0] == "absmax_kernel" for l in launches) else "logmel_kernel<1>"   # two-pass / single-pass step
-idx = [i for i, l in enumerate(launches) if l[0] == first]
-mid = len(idx) // 2
-step = [l for l in launches[idx[mid]:idx[mid + 1]] if not l[0].startswith("at::")]
+# the single-pass step: logmel_kernel<1> followed by the three separable-conv launches (the lengths / mask kernel runs on a side
+# stream and may land anywhere among them); the occurrence in the middle of the run
+def is_conv(n):
+    return n.startswith("sepconv")
+cands = []
+for i, l in enumerate(launches):
+    if l[0] == "logmel_kernel<1>":
+        win = [x for x in launches[i + 1:i + 7] if not x[0].startswith("at::")]
+        convs = [x for x in win if is_conv(x[0])][:3]
+        if len(convs) == 3:
+            extra = [x for x in win[:5] if "lengths_mask" in x[0]][:1]
+            cands.append([l] + convs + extra)
+step = max(cands, key=lambda c: sum(x[3] for x in c)) if cands else []   # (the capture warm-ups run on empty buffers: take the real batch)
 total = sum(l[3] for l in step)
 
 # ---- --set full -----------------------------------------------------------------------------------
@@ -102,6 +111,18 @@ with open(os.path.join(P, f"{name}_summary.md"), "w") as fh:
     fh.write("## `--set full` (per launch)\n\n| kernel | " + " | ".join(l for l, _ in want) + " |\n|---|" + "---:|" * len(want) + "\n")
     for k, vals in full:
         fh.write(f"| {k} | " + " | ".join((f"{vals[l]:.1f}" if isinstance(vals[l], float) else str(vals[l])) for l, _ in want) + " |\n")
+    fh.write("\n## Warp stall samples (`smsp__pcsamp_warps_issue_stalled_*`, share of all samples, top 7 per kernel)\n\n")
+    for row in r[2:]:
+        k = row[col["Kernel Name"]].replace("<unnamed>::", "").replace("void ", "").split("(")[0]
+        st = {}
+        for n, i in col.items():
+            if n.startswith("smsp__pcsamp_warps_issue_stalled_") and not n.endswith("_not_issued") and row[i]:
+                try:
+                    st[n.replace("smsp__pcsamp_warps_issue_stalled_", "")] = float(row[i].replace(",", ""))
+                except ValueError:
+                    pass
+        tot = sum(st.values()) or 1.0
+        fh.write(f"* `{k}`: " + ", ".join(f"{n} {100 * v / tot:.0f} %" for n, v in sorted(st.items(), key=lambda x: -x[1])[:7]) + "\n")
     fh.write("\n")
 
 with open(os.path.join(P, "traffic.json"), "w") as fh:
