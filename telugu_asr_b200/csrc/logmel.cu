@@ -43,7 +43,9 @@ constexpr int kWavSlots = kWavSmem / 4 / kThreads + 1;   // float4 slots per thr
 constexpr int kScrStride = 17;          // float2 units; odd -> conflict-free transposed reads
 constexpr int kScrPerFrame = 16 * kScrStride;
 constexpr int kPStride = kBins + 4;     // 261, odd; columns 257..260 stay zero (band padding of the generic path)
-constexpr int kChunkUtt = 1024;         // utterances whose work items are indexed at a time (4 per thread)
+constexpr int kChunkUtt = 256;          // utterances whose work items are indexed at a time (one per thread)
+constexpr int kListN = 32;              // located tiles per refill of the shared list
+constexpr int kRawFloats = 5368;        // TMA landing buffer of the next tile: 4 floats ahead of the tile's first sample + 5360
 
 struct __align__(16) Smem {
   float wav[kWavSmem];
@@ -53,9 +55,15 @@ struct __align__(16) Smem {
   int32_t vcum[kChunkUtt + 1];             // exclusive prefix of valid 32-frame tiles per utterance of the chunk
   int32_t pcum[kChunkUtt + 1];             // exclusive prefix of 128-row padding chunks per utterance
   int32_t wsum[2][kWarps];
-  int4 list[kThreads];                     // this CTA's next valid tiles: (utterance within chunk, tile index, len, -)
-  float4 band_w[kMelBandMaxW4];            // generic path only
-  MelBands bands;                          // generic path only
+  int4 list[kListN];                       // this CTA's next valid tiles: (utterance within chunk, tile index, len, -)
+  unsigned long long bar;                  // mbarrier of the raw-sample copies
+  union {
+    struct {
+      float4 band_w[kMelBandMaxW4];        // generic mel path only (no TMA staging there)
+      MelBands bands;
+    } gen;
+    float raw[kRawFloats];                 // fixed mel path: the next tile's raw samples, written by cp.async.bulk (TMA)
+  };
 };
 static_assert(sizeof(float) * kTileFrames * kOutStride <= sizeof(float2) * kWarps * 2 * kScrPerFrame,
               "output staging must fit in the transpose scratch");
@@ -99,6 +107,38 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 }
 #define X16(v, k) (v)[((k) >> 2) + 4 * ((k) & 3)]
 
+// ---- TMA (cp.async.bulk) staging of the raw samples ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void raw_bar_init(uint32_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void raw_bar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+// One thread: bulk-copy the samples a tile stages — [s0 - 4, s0 + count) of the utterance's row (the 4 floats ahead carry the
+// pre-emphasis neighbour of the first sample; none for the utterance's first tile) — so that sample s0 lands at raw[4].
+__device__ __forceinline__ void raw_issue(const LogmelArgs& a, float* raw, uint32_t bar, int b, int tf, int n) {
+  const int Tb = frames_of(n, a);
+  const int f0 = tf * kTileFrames;
+  const int nvalid = min(kTileFrames, Tb - f0);
+  const int s0 = f0 * kFrameStep;
+  const int count = (nvalid - 1) * kFrameStep + kFrameLen;
+  const int pre = s0 > 0 ? 4 : 0;
+  const uint32_t bytes = (uint32_t)(count + pre) * 4u;
+  const float* src = a.wav + (size_t)b * a.row_stride + (s0 - pre);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(raw + 4 - pre)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 template <bool FIXED>
 __global__ void __launch_bounds__(kThreads, 2)
 logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelFixedW mw) {
@@ -119,11 +159,17 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
   for (int k2 = 1; k2 < 16; ++k2) tw[k2] = a.tw256[(t * k2) & 255];
   const int partner = (lane & 16) | ((16 - t) & 15);
 
+  // TMA staging (fixed mel path, frames fully inside the signal): the next tile's raw samples are bulk-copied into S.raw while this
+  // tile computes; the staging pass then reads them from shared memory instead of waiting for global loads.
+  const bool use_tma = FIXED && !a.pad_end;
+  const uint32_t raw_bar = smem_addr(&S.bar);
+  uint32_t raw_phase = 0;
+  if (use_tma && tid == 0) raw_bar_init(raw_bar);
   for (int i = tid; i <= 128; i += kThreads) S.tw512[i] = a.tw512[i];
   if (!FIXED) {
-    for (int i = tid; i < kMelBandMaxW4; i += kThreads) S.band_w[i] = a.band_w[i];
+    for (int i = tid; i < kMelBandMaxW4; i += kThreads) S.gen.band_w[i] = a.band_w[i];
     const int32_t* src = reinterpret_cast<const int32_t*>(a.bands);
-    int32_t* dst = reinterpret_cast<int32_t*>(&S.bands);
+    int32_t* dst = reinterpret_cast<int32_t*>(&S.gen.bands);
     for (int i = tid; i < (int)(sizeof(MelBands) / 4); i += kThreads) dst[i] = src[i];
     for (int i = tid; i < kTileFrames * 4; i += kThreads) S.P[(i >> 2) * kPStride + kBins + (i & 3)] = 0.0f;
   }
@@ -142,10 +188,12 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
   for (int cb = 0; cb < a.B; cb += kChunkUtt) {
   const int nu = min(kChunkUtt, a.B - cb);
   {
-    int vt[4], pt[4], vs = 0, ps = 0;
+    constexpr int kPer = kChunkUtt / kThreads;     // utterances per thread
+    static_assert(kPer >= 1 && kPer * kThreads == kChunkUtt, "kChunkUtt must be a multiple of the block size");
+    int vt[kPer], pt[kPer], vs = 0, ps = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int u = 4 * tid + i;
+    for (int i = 0; i < kPer; ++i) {
+      const int u = kPer * tid + i;
       vt[i] = pt[i] = 0;
       if (u < nu) {
         const int Tu = frames_of(a.len[cb + u], a);
@@ -167,10 +215,10 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
     for (int w = 0; w < warp; ++w) { vb += S.wsum[0][w]; pb += S.wsum[1][w]; }
     if (tid == 0) { S.vcum[0] = 0; S.pcum[0] = 0; }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kPer; ++i) {
       vb += vt[i]; pb += pt[i];
-      S.vcum[4 * tid + i + 1] = vb;
-      S.pcum[4 * tid + i + 1] = pb;
+      S.vcum[kPer * tid + i + 1] = vb;
+      S.pcum[kPer * tid + i + 1] = pb;
     }
     __syncthreads();
   }
@@ -200,20 +248,21 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
   // shared list (utterance, tile index) that the tile loop then just reads.
 #pragma unroll 1
   while (jv < voff + vtot) {
-  const int nlist = min(kThreads, (voff + vtot - jv + (int)gridDim.x - 1) / (int)gridDim.x);
+  const int nlist = min(kListN, (voff + vtot - jv + (int)gridDim.x - 1) / (int)gridDim.x);
   if (tid < nlist) {
     const int x = jv - voff + tid * (int)gridDim.x;
     const int u = find(S.vcum, x);
     S.list[tid] = make_int4(u, x - S.vcum[u], a.len[cb + u], 0);   // the length rides along: no global load in the tile loop
   }
   __syncthreads();
+  if (use_tma && tid == 0) { const int4 it0 = S.list[0]; raw_issue(a, S.raw, raw_bar, cb + it0.x, it0.y, it0.z); }
 #pragma unroll 1
   for (int li = 0; li < nlist; ++li) {
     const int4 item = S.list[li];
     const int b = cb + item.x;
     const int tf = item.y;
 
-    if (li + 1 < nlist && tid < 168) {  // next tile -> L2: 5360 samples = 167.5 lines of 128 B
+    if (!use_tma && li + 1 < nlist && tid < 168) {  // next tile -> L2: 5360 samples = 167.5 lines of 128 B
       const int4 nxt = S.list[li + 1];
       const float* nrow = a.wav + (size_t)(cb + nxt.x) * a.row_stride;
       const int ns = nxt.y * kTileFrames * kFrameStep + tid * 32;
@@ -242,6 +291,20 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
       const float c = a.preemph;
       float4 x[kWavSlots];
       float xp[kWavSlots];
+      if (use_tma) {
+        raw_bar_wait(raw_bar, raw_phase);       // this tile's samples have landed in S.raw (copied while the previous tile computed)
+        raw_phase ^= 1u;
+#pragma unroll
+        for (int u = 0; u < kWavSlots; ++u) {
+          const int i4 = tid + u * kThreads;
+          x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          xp[u] = 0.0f;
+          if (4 * i4 < lim) {
+            x[u] = *reinterpret_cast<const float4*>(S.raw + 4 + 4 * i4);
+            if (s0 + 4 * i4 > 0) xp[u] = S.raw[3 + 4 * i4];
+          }
+        }
+      } else {
 #pragma unroll
       for (int u = 0; u < kWavSlots; ++u) {     // all loads first: 6 x 128-bit + 6 x 32-bit in flight per thread
         const int i4 = tid + u * kThreads;
@@ -252,6 +315,7 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
           x[u] = *reinterpret_cast<const float4*>(row + s);   // (rows are padded to 4 samples: in bounds)
           if (s > 0) xp[u] = row[s - 1];
         }
+      }
       }
       if (a.peak_out != nullptr) {
         // Single pass: max|x| of the samples this tile stages (slots beyond `lim` hold zeros); the tile that holds the
@@ -298,6 +362,10 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
       }
     }
     __syncthreads();
+    if (use_tma && tid == 0 && li + 1 < nlist) {   // every thread has its slots of S.raw in registers: the next tile's copy may overwrite it
+      const int4 nxt = S.list[li + 1];
+      raw_issue(a, S.raw, raw_bar, cb + nxt.x, nxt.y, nxt.z);
+    }
 
     // ---- FFT + power: two frames per warp per pass ------------------------------------------
 #pragma unroll 1
@@ -383,8 +451,8 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
       } else {
 #pragma unroll 1
         for (int m = warp; m < kMel; m += kWarps) {
-          const int k0 = S.bands.k0[m], n4 = S.bands.n4[m];
-          const float4* wp = S.band_w + S.bands.off4[m];
+          const int k0 = S.gen.bands.k0[m], n4 = S.gen.bands.n4[m];
+          const float4* wp = S.gen.band_w + S.gen.bands.off4[m];
           const float* pp = Prow + k0;
           float acc = 0.0f;
           for (int i = 0; i < n4; ++i) {
