@@ -161,7 +161,7 @@ logmel_kernel(const __grid_constant__ LogmelArgs a, const __grid_constant__ MelF
 
   // TMA staging (fixed mel path, frames fully inside the signal): the next tile's raw samples are bulk-copied into S.raw while this
   // tile computes; the staging pass then reads them from shared memory instead of waiting for global loads.
-  const bool use_tma = FIXED && !a.pad_end;
+  const bool use_tma = FIXED && !a.pad_end && a.tma != 0;
   const uint32_t raw_bar = smem_addr(&S.bar);
   uint32_t raw_phase = 0;
   if (use_tma && tid == 0) raw_bar_init(raw_bar);
@@ -530,6 +530,7 @@ static int logmel_launch(const TasrFeaturizer* f, const float* wav, const int32_
   a.pad_end = f->p.pad_end ? 1 : 0;
   a.mode = (f->p.feature_type == TASR_FEAT_SPECTROGRAM) ? 1 : 0;
   a.pad_fill_rows = pad_fill_rows;
+  { const char* e = getenv("TASR_LOGMEL_TMA"); a.tma = (e && atoi(e) == 0) ? 0 : 1; }
   a.preemph = f->p.preemphasis; a.floor_ = f->p.output_floor; a.log_scale = f->log_scale;
   if (peak_out) {
     a.floor_ = 0.0f;   // the floor is applied by the reader, after the gain (lg2(0) = -inf survives the addition)

@@ -57,6 +57,8 @@ struct LogmelArgs {
   int32_t normalize;
   int32_t pad_end;         // tf.signal.stft(pad_end=True): ceil(N/160) frames, the tail zero padded
   int32_t mode;            // 0: mel projection + log; 1: log of the first 80 power bins ("spectrogram")
+  int32_t tma;             // 1: the fixed-filterbank kernel stages the next tile's raw samples by cp.async.bulk (default; TASR_LOGMEL_TMA=0
+                           // at launch selects the register-staged global loads, bit-identical)
   int32_t pad_fill_rows;   // < 0: every collate padding row (t >= n_frames[b]) is written as 0.0; >= 0: only the first
                            // pad_fill_rows of them are guaranteed (lean mode: the rest of out[b] is left untouched)
   float preemph, floor_, log_scale;

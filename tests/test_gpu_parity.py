@@ -1040,6 +1040,27 @@ def test_persistent_kernel_applies_the_deferred_gain_bitwise(cuda_device, monkey
     assert not torch.isnan(res["1"][0]).any()
 
 
+def test_logmel_tma_staging_is_bit_identical_to_register_staging(cuda_device, monkeypatch):
+    """logmel_kernel brings the next tile's raw samples in by TMA (cp.async.bulk onto an mbarrier) and stages them from shared
+    memory; TASR_LOGMEL_TMA=0 keeps the register-staged global loads.  Same arithmetic on the same values: identical bits, two-pass
+    and single-pass, ragged lengths including utterances of one frame, exactly one tile, and one tile + one frame."""
+    from telugu_asr_b200.synth import draw_lengths
+    lens = draw_lengths(48, 400, 240000, seed=5)
+    lens[0], lens[1], lens[2], lens[3], lens[4] = 400, 399, 400 + 31 * 160, 400 + 32 * 160, 240000
+    wav, ln = oracle.make_waveforms(lens, seed=5, dist="tilt")
+    w, l = gpu(wav, cuda_device), gpu(ln, cuda_device)
+    feat = tasr.SpeechFeaturizer(**tasr.REFERENCE_SPEECH_CONFIG)
+    res = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("TASR_LOGMEL_TMA", tma)
+        two = feat.featurize_batch(w, l)
+        one = feat.featurize_batch(w, l, single_pass=True)
+        torch.cuda.synchronize()
+        res[tma] = (two[0].clone(), two[1].clone(), one[0].clone(), one[1].clone())
+    for a, b in zip(res["1"], res["0"]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("roles", ["18", "116"])
 def test_persistent_kernel_role_counts_are_bit_identical(cuda_device, monkeypatch, roles):
     """The persistent kernel's other role counts (one depthwise group; sixteen epilogue warps — TASR_WS_ROLES at plan creation) must
